@@ -1,0 +1,793 @@
+// glome_cuda.cu -- sm_100a kernels and the C-ABI of libglomecuda.so (include/glome_cuda.h).
+//
+// Kernels:
+//   K1 traverse   rayint / shadow over BIH, Mesh BVH and the scene graph      (glome_device.cuh)
+//   K2 shade      trace + materialShader (shadow rays, Blinn, reflect/refract/warp)
+//   K3 adaptive AA: per pass, a decide kernel (edge detect + warp-ballot/prefix compaction into a
+//      ray queue) and the persistent trace kernel that drains the queue
+//   K4 pack       rgbf / blitTile
+// The trace kernel is persistent: one grid sized to the SM count, warps pull 32-sample chunks
+// from an atomic counter, so queue lengths never travel to the host.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "glome_device.cuh"
+
+using namespace gdev;
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+extern "C" const char* glome_last_error(void) { return g_err.c_str(); }
+void glome_set_error(const std::string& s) { g_err = s; }
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e_);                            \
+            return GLOME_ECUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// device-side helpers shared by kernels
+// ---------------------------------------------------------------------------------------------
+struct TileGeom {
+    int width, height, bs, ntx, nty;
+    int nbx, nby;          // 8x4 micro-tiles per tile
+    int slots_per_tile;    // nbx*nby*32
+};
+__host__ __device__ inline TileGeom make_geom(int width, int height, int bs) {
+    TileGeom g;
+    g.width = width; g.height = height; g.bs = bs;
+    g.ntx = (width + bs - 1) / bs;   // chunk (Glome.hs:371-377): tiles start at k*bs, last one partial
+    g.nty = (height + bs - 1) / bs;
+    g.nbx = (bs + 7) / 8; g.nby = (bs + 3) / 4;
+    g.slots_per_tile = g.nbx * g.nby * 32;
+    return g;
+}
+// tile index in renderTiles' enumeration order: x chunks outer, y chunks inner (Glome.hs:384)
+__device__ __forceinline__ void tile_rect(const TileGeom& g, int ti, int& xt, int& yt, int& tw, int& th) {
+    int tx = ti / g.nty, ty = ti % g.nty;
+    xt = tx * g.bs; yt = ty * g.bs;
+    tw = min(g.bs, g.width - xt); th = min(g.bs, g.height - yt);
+}
+
+struct TC { Flt r, g, b, a, d; };  // TColor (Glome.hs:153)
+__device__ __forceinline__ TC ld_tc(const double* __restrict__ buf, size_t pix) {
+    const double* p = buf + pix * 5;
+    TC c; c.r = p[0]; c.g = p[1]; c.b = p[2]; c.a = p[3]; c.d = p[4];
+    return c;
+}
+__device__ __forceinline__ void st_tc(double* __restrict__ buf, size_t pix, const TC& c) {
+    double* p = buf + pix * 5;
+    p[0] = c.r; p[1] = c.g; p[2] = c.b; p[3] = c.a; p[4] = c.d;
+}
+__device__ __forceinline__ Flt cCmp(const TC& p, const TC& q) {  // Glome.hs:179-189
+    Flt md;
+    if (p.d == 0 && q.d == 0) md = 0;
+    else md = (p.d > q.d) ? (p.d / q.d) - 1 : (q.d / p.d) - 1;
+    return fabs_(q.r - p.r) + fabs_(q.g - p.g) + fabs_(q.b - p.b) + fabs_(q.a - p.a) + md;
+}
+__device__ __forceinline__ TC cAvg(const TC& a, const TC& b, const TC& c, const TC& d) {  // Glome.hs:191-197
+    TC r;
+    r.r = (a.r + b.r + c.r + d.r) * 0.25; r.g = (a.g + b.g + c.g + d.g) * 0.25; r.b = (a.b + b.b + c.b + d.b) * 0.25;
+    r.a = (a.a + b.a + c.a + d.a) * 0.25; r.d = (a.d + b.d + c.d + d.d) * 0.25;
+    return r;
+}
+__device__ __forceinline__ TC cAvg2(const TC& a, const TC& b) {  // Glome.hs:199-205
+    TC r;
+    r.r = (a.r + b.r) * 0.5; r.g = (a.g + b.g) * 0.5; r.b = (a.b + b.b) * 0.5; r.a = (a.a + b.a) * 0.5; r.d = (a.d + b.d) * 0.5;
+    return r;
+}
+__device__ __forceinline__ TC tc_init() { TC c; c.r = 0; c.g = 0; c.b = 0; c.a = 0; c.d = GLM_INFINITY; return c; }
+// getc (Glome.hs:233-235): outside the TILE -> (0,0,0,0,infinity)
+__device__ __forceinline__ TC getc(const double* __restrict__ v, int width, int xt, int yt, int tw, int th, int x, int y) {
+    if ((x >= xt) && (x < xt + tw) && (y >= yt) && (y < yt + th)) return ld_tc(v, (size_t)y * width + x);
+    return tc_init();
+}
+// pass-5 output (Glome.hs:309-316)
+__device__ __forceinline__ TC pass5_combine(const TC& color, const TC& a, const TC& b, const TC& c, const TC& d, bool lastx,
+                                            bool lasty) {
+    if (lastx) {
+        if (lasty) return color;
+        return cAvg2(color, cAvg2(a, b));
+    }
+    if (lasty) return cAvg2(color, cAvg2(a, d));
+    return cAvg2(color, cAvg(a, b, c, d));
+}
+__device__ __forceinline__ Flt cap1(Flt x) { return (x >= 1) ? 1 - GLM_DELTA : x; }  // Glome.hs:98
+__device__ __forceinline__ uint32_t rgbf(Flt r, Flt g, Flt b) {                       // Glome.hs:107 (Word32 arithmetic)
+    uint32_t R = (uint32_t)(long long)floor(cap1(r) * 256);
+    uint32_t G = (uint32_t)(long long)floor(cap1(g) * 256);
+    uint32_t B = (uint32_t)(long long)floor(cap1(b) * 256);
+    return R * 65536u + G * 256u + B;
+}
+
+struct DevStats {  // accumulated with atomics
+    unsigned long long primary, shadow, secondary, overflow, perlin_range;
+};
+
+__device__ __forceinline__ void flush_counters(DevStats* st, unsigned int primary, const RayCounters& rc, unsigned int ovf) {
+    // warp-reduce then one atomic per warp and counter
+    unsigned int vals[5] = {primary, rc.shadow, rc.secondary, ovf, rc.perlin_range};
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        unsigned int v = vals[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        vals[k] = v;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (vals[0]) atomicAdd(&st->primary, (unsigned long long)vals[0]);
+        if (vals[1]) atomicAdd(&st->shadow, (unsigned long long)vals[1]);
+        if (vals[2]) atomicAdd(&st->secondary, (unsigned long long)vals[2]);
+        if (vals[3]) atomicAdd(&st->overflow, (unsigned long long)vals[3]);
+        if (vals[4]) atomicAdd(&st->perlin_range, (unsigned long long)vals[4]);
+    }
+}
+
+__device__ __forceinline__ void hit_out(const Hit& h, GlomeHit* o) {
+    o->t = ridepth(h);
+    o->hit = h.hit;
+    o->prim = h.hit ? h.prim : -1;
+    o->sub = h.hit ? h.sub : -1;
+    o->flags = h.flags;
+    o->ntex = h.hit ? h.tex.n : 0;
+    o->ntag = h.hit ? h.tag.n : 0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { o->pos[i] = 0; o->norm[i] = 0; }
+    if (h.hit) {
+        o->pos[0] = h.pos.x; o->pos[1] = h.pos.y; o->pos[2] = h.pos.z;
+        o->norm[0] = h.norm.x; o->norm[1] = h.norm.y; o->norm[2] = h.norm.z;
+    }
+#pragma unroll
+    for (int i = 0; i < GLOME_MAX_STACK; i++) {
+        o->tex[i] = (h.hit && i < h.tex.n) ? h.tex.v[i] : 0;
+        o->tag[i] = (h.hit && i < h.tag.n) ? h.tag.v[i] : 0;
+    }
+}
+
+__device__ __forceinline__ Ray ld_ray(const double* __restrict__ rays, long long i) {
+    const double* p = rays + 6 * i;
+    return mkray(vec(p[0], p[1], p[2]), vec(p[3], p[4], p[5]));
+}
+
+// ---------------------------------------------------------------------------------------------
+// batch query kernels (parity surfaces)
+// ---------------------------------------------------------------------------------------------
+template <bool GEN>
+__global__ void __launch_bounds__(128) k_rayint_batch(DScene S, long long n, const double* __restrict__ rays,
+                                                      const double* __restrict__ tmax, int stride, GlomeHit* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        Hit h;
+        rayint_scene<GEN>(S, S.root, ld_ray(rays, i), tmax[stride ? i : 0], h);
+        hit_out(h, out + i);
+    }
+}
+template <bool GEN>
+__global__ void __launch_bounds__(128) k_shadow_batch(DScene S, long long n, const double* __restrict__ rays,
+                                                      const double* __restrict__ tmax, int stride, uint8_t* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = shadow_scene<GEN>(S, S.root, ld_ray(rays, i), tmax[stride ? i : 0]) ? 1 : 0;
+}
+__global__ void __launch_bounds__(128) k_inside_batch(DScene S, long long n, const double* __restrict__ pts,
+                                                      uint8_t* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = inside_node(S, S.root, vec(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2])) ? 1 : 0;
+}
+template <bool GEN>
+__global__ void __launch_bounds__(128) k_trace_batch(DScene S, long long n, const double* __restrict__ rays,
+                                                     const double* __restrict__ tmax, int stride, int recurs,
+                                                     double* __restrict__ rgba, double* __restrict__ depth,
+                                                     GlomeHit* __restrict__ hits, DevStats* st) {
+    RayCounters rc = {0, 0, 0};
+    unsigned int ovf = 0, prim = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        ColorA c;
+        Hit h;
+        trace<GEN>(S, 0, S.root, ld_ray(rays, i), tmax[stride ? i : 0], recurs, c, h, rc);
+        rgba[4 * i] = c.r; rgba[4 * i + 1] = c.g; rgba[4 * i + 2] = c.b; rgba[4 * i + 3] = c.a;
+        depth[i] = ridepth(h);
+        if (hits) hit_out(h, hits + i);
+        if (h.flags) ovf++;
+        prim++;
+    }
+    __syncwarp();
+    flush_counters(st, prim, rc, ovf);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2/K3: the persistent sample tracer.
+//   MODE 0: one ray per pixel over the selected tiles (renderTile, Glome.hs:162-176); work items
+//           are 8x4 micro-tiles of each tile so a warp's rays are coherent.
+//   MODE 1: adaptive-AA passes 1-4: queue of pixel ids, sample at getCoords x y, write v.
+//   MODE 5: adaptive-AA pass 5: queue of pixel ids, sample at (x+0.5, y+0.5), write v2 via
+//           pass5_combine.
+// ---------------------------------------------------------------------------------------------
+struct TraceParams {
+    TileGeom g;
+    DCamera cam;
+    int recurs, tint;
+    int tile_first, tile_stride, n_sel;  // selected tiles: ti = tile_first + k*tile_stride
+    const int* queue;                    // MODE 1/5
+    const int* queue_count;
+    unsigned int* work_counter;          // zeroed before launch
+    const double* v;                     // MODE 5 reads
+    double* out;                         // MODE 0/1: v ; MODE 5: v2
+    DevStats* st;
+};
+
+template <bool GEN, int MODE>
+__global__ void __launch_bounds__(GEN ? 64 : 128) k_trace_samples(DScene S, TraceParams P) {
+    const int lane = threadIdx.x & 31;
+    RayCounters rc = {0, 0, 0};
+    unsigned int ovf = 0, nprim = 0;
+    const long long total = (MODE == 0) ? (long long)P.n_sel * P.g.slots_per_tile : (long long)(*P.queue_count);
+    for (;;) {
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(P.work_counter, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if ((long long)base >= total) break;
+        long long w = (long long)base + lane;
+        bool valid = w < total;
+        int x = 0, y = 0;
+        if (MODE == 0) {
+            if (valid) {
+                int k = (int)(w / P.g.slots_per_tile), local = (int)(w % P.g.slots_per_tile);
+                int ti = P.tile_first + k * P.tile_stride;
+                int xt, yt, tw, th;
+                tile_rect(P.g, ti, xt, yt, tw, th);
+                int blk = local >> 5, l = local & 31;
+                int px = (blk % P.g.nbx) * 8 + (l & 7), py = (blk / P.g.nbx) * 4 + (l >> 3);
+                valid = px < tw && py < th;
+                x = xt + px; y = yt + py;
+            }
+        } else if (valid) {
+            int pix = P.queue[w];
+            x = pix % P.g.width; y = pix / P.g.width;
+        }
+        if (valid) {
+            Flt xc, yc;
+            if (MODE == 5) getCoordsf(P.g.width, P.g.height, (Flt)x + 0.5, (Flt)y + 0.5, xc, yc);
+            else getCoordsf(P.g.width, P.g.height, (Flt)x, (Flt)y, xc, yc);
+            ColorA c;
+            Hit h;
+            trace<GEN>(S, 0, S.root, camera_ray(P.cam, xc, yc), GLM_INFINITY, P.recurs, c, h, rc);
+            nprim++;
+            if (h.flags) ovf++;
+            TC col;
+            col.r = c.r; col.g = c.g; col.b = c.b; col.a = c.a; col.d = ridepth(h);
+            size_t pix = (size_t)y * P.g.width + x;
+            if (MODE == 0) {
+                if (P.tint) col.r = col.r + (col.d / 400);  // Glome.hs:174
+                st_tc(P.out, pix, col);
+            } else if (MODE == 1) {
+                st_tc(P.out, pix, col);
+            } else {
+                int tx = x / P.g.bs, ty = y / P.g.bs;
+                int xt = tx * P.g.bs, yt = ty * P.g.bs;
+                int tw = min(P.g.bs, P.g.width - xt), th = min(P.g.bs, P.g.height - yt);
+                TC a = getc(P.v, P.g.width, xt, yt, tw, th, x, y), b = getc(P.v, P.g.width, xt, yt, tw, th, x, y + 1);
+                TC cc = getc(P.v, P.g.width, xt, yt, tw, th, x + 1, y + 1), d = getc(P.v, P.g.width, xt, yt, tw, th, x + 1, y);
+                st_tc(P.out, pix, pass5_combine(col, a, b, cc, d, x == xt + tw - 1, y == yt + th - 1));
+            }
+        }
+    }
+    __syncwarp();
+    flush_counters(P.st, nprim, rc, ovf);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: adaptive-AA decide kernels (Glome.hs:226-323).  One block per selected tile.  Each
+// candidate pixel of the pass either gets the average of its neighbours or is appended to the
+// ray queue; queue slots are handed out per warp with ballot + popc prefix and one atomicAdd.
+// ---------------------------------------------------------------------------------------------
+struct DecideParams {
+    TileGeom g;
+    int tile_first, tile_stride;
+    int pass;            // 1..5
+    Flt threshold;
+    double* v;           // pass 1 initialises it; passes 2-4 write averages into it
+    double* v2;          // pass 5 writes averages into it
+    int* queue;
+    int* queue_count;    // zeroed before launch
+};
+
+__global__ void __launch_bounds__(256) k_aa_decide(DecideParams P) {
+    int ti = P.tile_first + blockIdx.x * P.tile_stride;
+    int xt, yt, tw, th;
+    tile_rect(P.g, ti, xt, yt, tw, th);
+    const int width = P.g.width;
+    const int npix = tw * th;
+    const int lane = threadIdx.x & 31;
+    for (int base = 0; base < npix; base += blockDim.x) {
+        int i = base + threadIdx.x;
+        bool need = false;
+        int x = 0, y = 0;
+        if (i < npix) {
+            int dx = i % tw, dy = i / tw;
+            x = xt + dx; y = yt + dy;
+            size_t pix = (size_t)y * width + x;
+            bool member;
+            switch (P.pass) {
+                case 1: member = ((dx | dy) & 1) == 0 && ((dx + dy) & 3) == 0; break;   // Glome.hs:241-250
+                case 2: member = ((dx | dy) & 1) == 0 && ((dx + dy) & 3) == 2; break;   // :251-262
+                case 3: member = (dx & 1) && (dy & 1); break;                           // :272-281
+                case 4: member = ((dx + dy) & 1) == 1; break;                           // :283-295
+                default: member = true; break;                                          // :301-319
+            }
+            if (P.pass == 1) {
+                st_tc(P.v, pix, tc_init());  // MUV.replicate (0,0,0,0,infinity) (:231)
+                need = member;
+            } else if (member) {
+                TC a, b, c, d;
+                if (P.pass == 2) {
+                    a = getc(P.v, width, xt, yt, tw, th, x - 2, y); b = getc(P.v, width, xt, yt, tw, th, x, y + 2);
+                    c = getc(P.v, width, xt, yt, tw, th, x + 2, y); d = getc(P.v, width, xt, yt, tw, th, x, y - 2);
+                } else if (P.pass == 3) {
+                    a = getc(P.v, width, xt, yt, tw, th, x - 1, y - 1); b = getc(P.v, width, xt, yt, tw, th, x + 1, y - 1);
+                    c = getc(P.v, width, xt, yt, tw, th, x + 1, y + 1); d = getc(P.v, width, xt, yt, tw, th, x - 1, y + 1);
+                } else if (P.pass == 4) {
+                    a = getc(P.v, width, xt, yt, tw, th, x - 1, y); b = getc(P.v, width, xt, yt, tw, th, x, y + 1);
+                    c = getc(P.v, width, xt, yt, tw, th, x + 1, y); d = getc(P.v, width, xt, yt, tw, th, x, y - 1);
+                } else {
+                    a = getc(P.v, width, xt, yt, tw, th, x, y); b = getc(P.v, width, xt, yt, tw, th, x, y + 1);
+                    c = getc(P.v, width, xt, yt, tw, th, x + 1, y + 1); d = getc(P.v, width, xt, yt, tw, th, x + 1, y);
+                }
+                Flt variance = fmax_(cCmp(a, c), cCmp(b, d));  // decide (Glome.hs:213-219)
+                if (variance > P.threshold) need = true;
+                else {
+                    TC avg = cAvg(a, b, c, d);
+                    if (P.pass == 5) st_tc(P.v2, pix, pass5_combine(avg, a, b, c, d, x == xt + tw - 1, y == yt + th - 1));
+                    else st_tc(P.v, pix, avg);
+                }
+            }
+        }
+        // warp-aggregated compaction
+        unsigned int m = __ballot_sync(0xffffffffu, need);
+        if (m) {
+            int leader = __ffs(m) - 1;
+            int slot = 0;
+            if (lane == leader) slot = atomicAdd(P.queue_count, __popc(m));
+            slot = __shfl_sync(0xffffffffu, slot, leader);
+            if (need) P.queue[slot + __popc(m & ((1u << lane) - 1))] = y * width + x;
+        }
+    }
+}
+
+// K4: blitTile / rgbf (Glome.hs:353-358, 107-110)
+__global__ void __launch_bounds__(256) k_pack_rgb8(TileGeom g, int tile_first, int tile_stride, const double* __restrict__ tc,
+                                                   uint32_t* __restrict__ rgb8) {
+    int ti = tile_first + blockIdx.x * tile_stride;
+    int xt, yt, tw, th;
+    tile_rect(g, ti, xt, yt, tw, th);
+    for (int i = threadIdx.x; i < tw * th; i += blockDim.x) {
+        size_t pix = (size_t)(yt + i / tw) * g.width + (xt + i % tw);
+        TC c = ld_tc(tc, pix);
+        rgb8[pix] = rgbf(c.r * c.a, c.g * c.a, c.b * c.a);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct GlomeScene {
+    int device;
+    int scene_class;
+    int sm_count;
+    DScene d;
+    std::vector<void*> bufs;
+    // render workspace (grown on demand)
+    double* v; double* v2; uint32_t* rgb8; size_t ws_pix;
+    int* queue; size_t queue_cap;
+    int* queue_count; unsigned int* work_counter; DevStats* stats;
+    // batch workspace
+    void* bw[4]; size_t bw_cap[4];
+    cudaEvent_t ev0, ev1;
+    int launches;
+    size_t stack_bytes;
+};
+
+extern "C" int glome_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+template <typename T, typename D>
+static int upload(GlomeScene* s, const T* src, size_t n, D* dst) {
+    void* p = nullptr;
+    size_t bytes = (n ? n : 1) * sizeof(T);
+    CK(cudaMalloc(&p, bytes));
+    s->bufs.push_back(p);
+    if (n) CK(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    *dst = (const T*)p;
+    return GLOME_OK;
+}
+
+static int validate(const GlomeFlatScene* d) {
+    if (!d || d->version != GLOME_FLAT_VERSION) { g_err = "FlatScene: bad version"; return GLOME_EINVAL; }
+    if (d->n_nodes <= 0 || d->root < 0 || d->root >= d->n_nodes) { g_err = "FlatScene: bad root"; return GLOME_EINVAL; }
+    for (int i = 0; i < d->n_nodes; i++) {
+        const GlomeNode& n = d->nodes[i];
+        if (n.type < 0 || n.type >= GLOME_NODE_TYPE_COUNT) { g_err = "FlatScene: bad node type"; return GLOME_EINVAL; }
+        bool bad = false;
+        switch (n.type) {
+            case GLOME_GROUP: case GLOME_INTERSECTION: bad = n.b < 0 || n.a < 0 || (long long)n.a + n.b > d->n_nodes; break;
+            case GLOME_INSTANCE: bad = n.a < 0 || n.a >= d->n_nodes || n.b < 0 || (long long)n.b + 24 > d->n_dpool; break;
+            case GLOME_DIFFERENCE: case GLOME_BOUND: case GLOME_INNERBOUND:
+                bad = n.a < 0 || n.a >= d->n_nodes || n.b < 0 || n.b >= d->n_nodes; break;
+            case GLOME_TEX: bad = n.a < 0 || n.a >= d->n_nodes || n.b < 0 || n.b >= d->n_textures; break;
+            case GLOME_TAG: case GLOME_NOSHADOW: case GLOME_ONLYSHADOW: bad = n.a < 0 || n.a >= d->n_nodes; break;
+            case GLOME_BIH: bad = n.b < 0 || (long long)n.b + 6 > d->n_dpool || (n.a >= 0 ? n.a >= d->n_bihnodes : ~n.a + 1 >= d->n_ipool); break;
+            case GLOME_MESH: bad = n.a < 0 || (long long)n.a + 12 > d->n_ipool; break;
+            case GLOME_VOID: break;
+            default: bad = n.a < 0 || n.a >= d->n_dpool; break;
+        }
+        if (bad) { g_err = "FlatScene: node " + std::to_string(i) + " has out-of-range payload"; return GLOME_EINVAL; }
+    }
+    if (d->n_lights > 0 && d->n_lightsets > 0) {
+        for (int i = 0; i < d->n_lightsets; i++)
+            if (d->lightsets[2 * i] < 0 || d->lightsets[2 * i] + d->lightsets[2 * i + 1] > d->n_lights ||
+                d->lightsets[2 * i + 1] > GDEV_MAX_LIGHTS) { g_err = "FlatScene: bad light set"; return GLOME_EINVAL; }
+    }
+    return GLOME_OK;
+}
+
+extern "C" int glome_scene_create(const GlomeFlatScene* desc, int device, GlomeScene** out) {
+    if (!out) { g_err = "null out"; return GLOME_EINVAL; }
+    *out = nullptr;
+    int rc = validate(desc);
+    if (rc) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        g_err = "no CUDA device: libglomecuda has no CPU fallback";
+        return GLOME_ENODEV;
+    }
+    if (device < 0 || device >= ndev) { g_err = "bad device index"; return GLOME_EINVAL; }
+    CK(cudaSetDevice(device));
+    GlomeScene* s = new GlomeScene();
+    s->device = device;
+    s->scene_class = desc->scene_class;
+    s->v = s->v2 = nullptr; s->rgb8 = nullptr; s->ws_pix = 0; s->queue = nullptr; s->queue_cap = 0;
+    for (int i = 0; i < 4; i++) { s->bw[i] = nullptr; s->bw_cap[i] = 0; }
+    s->launches = 0;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    s->sm_count = prop.multiProcessorCount;
+    memset(&s->d, 0, sizeof(s->d));
+    s->d.root = desc->root;
+    s->d.n_lights = desc->n_lights;
+    std::vector<int32_t> ls;
+    if (desc->n_lightsets > 0) ls.assign(desc->lightsets, desc->lightsets + 2 * desc->n_lightsets);
+    else { ls.push_back(0); ls.push_back(desc->n_lights); }
+    if ((rc = upload(s, desc->nodes, (size_t)desc->n_nodes, &s->d.nodes))) return rc;
+    if ((rc = upload(s, desc->bihnodes, (size_t)desc->n_bihnodes, &s->d.bih))) return rc;
+    if ((rc = upload(s, desc->bvhnodes, (size_t)desc->n_bvhnodes, &s->d.bvh))) return rc;
+    if ((rc = upload(s, desc->ipool, (size_t)desc->n_ipool, &s->d.ipool))) return rc;
+    if ((rc = upload(s, desc->dpool, (size_t)desc->n_dpool, &s->d.dpool))) return rc;
+    if ((rc = upload(s, desc->textures, (size_t)desc->n_textures, &s->d.textures))) return rc;
+    if ((rc = upload(s, desc->materials, (size_t)desc->n_materials, &s->d.materials))) return rc;
+    if ((rc = upload(s, desc->lights, (size_t)desc->n_lights, &s->d.lights))) return rc;
+    if ((rc = upload(s, ls.data(), ls.size(), &s->d.lightsets))) return rc;
+    CK(cudaMalloc((void**)&s->queue_count, sizeof(int)));
+    CK(cudaMalloc((void**)&s->work_counter, sizeof(unsigned int)));
+    CK(cudaMalloc((void**)&s->stats, sizeof(DevStats)));
+    CK(cudaEventCreate(&s->ev0));
+    CK(cudaEventCreate(&s->ev1));
+    // the general interpreter recurses: give its threads a deep stack
+    s->stack_bytes = 0;
+    if (s->scene_class == GLOME_CLASS_GENERAL) {
+        size_t want = 40 * 1024;
+        const char* e = getenv("GLOME_STACK_BYTES");
+        if (e) want = (size_t)atol(e);
+        CK(cudaDeviceSetLimit(cudaLimitStackSize, want));
+        s->stack_bytes = want;
+    }
+    *out = s;
+    return GLOME_OK;
+}
+
+extern "C" int glome_scene_destroy(GlomeScene* s) {
+    if (!s) return GLOME_OK;
+    cudaSetDevice(s->device);
+    for (void* p : s->bufs) cudaFree(p);
+    cudaFree(s->v); cudaFree(s->v2); cudaFree(s->rgb8); cudaFree(s->queue);
+    cudaFree(s->queue_count); cudaFree(s->work_counter); cudaFree(s->stats);
+    for (int i = 0; i < 4; i++) cudaFree(s->bw[i]);
+    cudaEventDestroy(s->ev0); cudaEventDestroy(s->ev1);
+    delete s;
+    return GLOME_OK;
+}
+
+static int grow(GlomeScene* s, int slot, size_t bytes) {
+    if (s->bw_cap[slot] >= bytes) return GLOME_OK;
+    if (s->bw[slot]) cudaFree(s->bw[slot]);
+    s->bw[slot] = nullptr; s->bw_cap[slot] = 0;
+    CK(cudaMalloc(&s->bw[slot], bytes));
+    s->bw_cap[slot] = bytes;
+    return GLOME_OK;
+}
+static int batch_grid(GlomeScene* s, long long n) {
+    long long blocks = (n + 127) / 128;
+    long long cap = (long long)s->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+extern "C" int glome_rayint_batch(GlomeScene* s, int64_t n, const double* rays, const double* tmax, int tmax_stride,
+                                  GlomeHit* out) {
+    if (!s || n < 0 || !rays || !tmax || !out) { g_err = "bad argument"; return GLOME_EINVAL; }
+    if (n == 0) return GLOME_OK;
+    CK(cudaSetDevice(s->device));
+    int rc;
+    size_t nt = tmax_stride ? (size_t)n : 1;
+    if ((rc = grow(s, 0, (size_t)n * 48))) return rc;
+    if ((rc = grow(s, 1, nt * 8))) return rc;
+    if ((rc = grow(s, 2, (size_t)n * sizeof(GlomeHit)))) return rc;
+    CK(cudaMemcpy(s->bw[0], rays, (size_t)n * 48, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->bw[1], tmax, nt * 8, cudaMemcpyHostToDevice));
+    int grid = batch_grid(s, n);
+    if (s->scene_class == GLOME_CLASS_FLAT)
+        k_rayint_batch<false><<<grid, 128>>>(s->d, n, (const double*)s->bw[0], (const double*)s->bw[1], tmax_stride, (GlomeHit*)s->bw[2]);
+    else
+        k_rayint_batch<true><<<grid, 128>>>(s->d, n, (const double*)s->bw[0], (const double*)s->bw[1], tmax_stride, (GlomeHit*)s->bw[2]);
+    s->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out, s->bw[2], (size_t)n * sizeof(GlomeHit), cudaMemcpyDeviceToHost));
+    return GLOME_OK;
+}
+
+extern "C" int glome_shadow_batch(GlomeScene* s, int64_t n, const double* rays, const double* tmax, int tmax_stride,
+                                  uint8_t* occluded) {
+    if (!s || n < 0 || !rays || !tmax || !occluded) { g_err = "bad argument"; return GLOME_EINVAL; }
+    if (n == 0) return GLOME_OK;
+    CK(cudaSetDevice(s->device));
+    int rc;
+    size_t nt = tmax_stride ? (size_t)n : 1;
+    if ((rc = grow(s, 0, (size_t)n * 48))) return rc;
+    if ((rc = grow(s, 1, nt * 8))) return rc;
+    if ((rc = grow(s, 2, (size_t)n))) return rc;
+    CK(cudaMemcpy(s->bw[0], rays, (size_t)n * 48, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->bw[1], tmax, nt * 8, cudaMemcpyHostToDevice));
+    int grid = batch_grid(s, n);
+    if (s->scene_class == GLOME_CLASS_FLAT)
+        k_shadow_batch<false><<<grid, 128>>>(s->d, n, (const double*)s->bw[0], (const double*)s->bw[1], tmax_stride, (uint8_t*)s->bw[2]);
+    else
+        k_shadow_batch<true><<<grid, 128>>>(s->d, n, (const double*)s->bw[0], (const double*)s->bw[1], tmax_stride, (uint8_t*)s->bw[2]);
+    s->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(occluded, s->bw[2], (size_t)n, cudaMemcpyDeviceToHost));
+    return GLOME_OK;
+}
+
+extern "C" int glome_inside_batch(GlomeScene* s, int64_t n, const double* pts, uint8_t* inside) {
+    if (!s || n < 0 || !pts || !inside) { g_err = "bad argument"; return GLOME_EINVAL; }
+    if (n == 0) return GLOME_OK;
+    CK(cudaSetDevice(s->device));
+    int rc;
+    if ((rc = grow(s, 0, (size_t)n * 24))) return rc;
+    if ((rc = grow(s, 2, (size_t)n))) return rc;
+    CK(cudaMemcpy(s->bw[0], pts, (size_t)n * 24, cudaMemcpyHostToDevice));
+    // inside recurses (inside_bih_rec ...): make sure the stack limit is generous for flat scenes too
+    if (s->stack_bytes == 0) { CK(cudaDeviceSetLimit(cudaLimitStackSize, 8 * 1024)); s->stack_bytes = 8 * 1024; }
+    k_inside_batch<<<batch_grid(s, n), 128>>>(s->d, n, (const double*)s->bw[0], (uint8_t*)s->bw[2]);
+    s->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(inside, s->bw[2], (size_t)n, cudaMemcpyDeviceToHost));
+    return GLOME_OK;
+}
+
+static void read_stats(GlomeScene* s, GlomeRenderStats* out, float ms, int launches) {
+    DevStats h;
+    memset(&h, 0, sizeof(h));
+    cudaMemcpy(&h, s->stats, sizeof(h), cudaMemcpyDeviceToHost);
+    if (!out) return;
+    out->rays_primary = (int64_t)h.primary;
+    out->rays_shadow = (int64_t)h.shadow;
+    out->rays_secondary = (int64_t)h.secondary;
+    out->overflow_rays = (int64_t)h.overflow;
+    out->perlin_range = (int64_t)h.perlin_range;
+    out->kernel_ms = ms;
+    out->launches = launches;
+    out->reserved = 0;
+}
+
+extern "C" int glome_trace_batch(GlomeScene* s, int64_t n, const double* rays, const double* tmax, int tmax_stride, int recurs,
+                                 double* rgba, double* depth, GlomeHit* hits) {
+    if (!s || n < 0 || !rays || !tmax || !rgba || !depth) { g_err = "bad argument"; return GLOME_EINVAL; }
+    if (n == 0) return GLOME_OK;
+    CK(cudaSetDevice(s->device));
+    int rc;
+    size_t nt = tmax_stride ? (size_t)n : 1;
+    if ((rc = grow(s, 0, (size_t)n * 48))) return rc;
+    if ((rc = grow(s, 1, nt * 8))) return rc;
+    if ((rc = grow(s, 2, (size_t)n * 40))) return rc;
+    if (hits && (rc = grow(s, 3, (size_t)n * sizeof(GlomeHit)))) return rc;
+    CK(cudaMemcpy(s->bw[0], rays, (size_t)n * 48, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->bw[1], tmax, nt * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemset(s->stats, 0, sizeof(DevStats)));
+    double* d_rgba = (double*)s->bw[2];
+    double* d_depth = d_rgba + 4 * n;
+    int grid = batch_grid(s, n);
+    if (s->scene_class == GLOME_CLASS_FLAT)
+        k_trace_batch<false><<<grid, 128>>>(s->d, n, (const double*)s->bw[0], (const double*)s->bw[1], tmax_stride, recurs, d_rgba,
+                                            d_depth, hits ? (GlomeHit*)s->bw[3] : nullptr, s->stats);
+    else
+        k_trace_batch<true><<<grid, 128>>>(s->d, n, (const double*)s->bw[0], (const double*)s->bw[1], tmax_stride, recurs, d_rgba,
+                                           d_depth, hits ? (GlomeHit*)s->bw[3] : nullptr, s->stats);
+    s->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(rgba, d_rgba, (size_t)n * 32, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(depth, d_depth, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    if (hits) CK(cudaMemcpy(hits, s->bw[3], (size_t)n * sizeof(GlomeHit), cudaMemcpyDeviceToHost));
+    return GLOME_OK;
+}
+
+extern "C" void glome_render_opts_default(GlomeRenderOpts* o) {
+    memset(o, 0, sizeof(*o));
+    o->mode = GLOME_MODE_ADAPTIVE_AA;  // the live path of the reference (Glome.hs:385)
+    o->blocksize = 65;                 // Glome.hs:116
+    o->recurs = 3;                     // Glome.hs:25
+    o->tint_depth = 0;
+    o->thresholds[0] = 0.14; o->thresholds[1] = 0.15; o->thresholds[2] = 0.16; o->thresholds[3] = 0.18;  // Glome.hs:221-224
+    o->tile_first = 0; o->tile_stride = 1; o->want_rgb8 = 0;
+}
+
+extern "C" int glome_tile_count(int width, int height, int blocksize) {
+    if (width <= 0 || height <= 0 || blocksize <= 0) return 0;
+    TileGeom g = make_geom(width, height, blocksize);
+    return g.ntx * g.nty;
+}
+extern "C" int glome_tile_rect(int width, int height, int blocksize, int i, int32_t rect[4]) {
+    if (width <= 0 || height <= 0 || blocksize <= 0) { g_err = "bad geometry"; return GLOME_EINVAL; }
+    TileGeom g = make_geom(width, height, blocksize);
+    if (i < 0 || i >= g.ntx * g.nty) { g_err = "tile index out of range"; return GLOME_EINVAL; }
+    int tx = i / g.nty, ty = i % g.nty;
+    rect[0] = tx * blocksize; rect[1] = ty * blocksize;
+    rect[2] = (blocksize < width - rect[0]) ? blocksize : width - rect[0];
+    rect[3] = (blocksize < height - rect[1]) ? blocksize : height - rect[1];
+    return GLOME_OK;
+}
+
+template <bool GEN, int MODE>
+static int launch_trace(GlomeScene* s, const TraceParams& P, cudaStream_t st) {
+    static int blocks_per_sm = 0;
+    const int threads = GEN ? 64 : 128;
+    if (!blocks_per_sm) {
+        int b = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace_samples<GEN, MODE>, threads, 0));
+        blocks_per_sm = b > 0 ? b : 1;
+    }
+    CK(cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned int), st));
+    k_trace_samples<GEN, MODE><<<s->sm_count * blocks_per_sm, threads, 0, st>>>(s->d, P);
+    s->launches++;
+    CK(cudaGetLastError());
+    return GLOME_OK;
+}
+template <int MODE>
+static int launch_trace_c(GlomeScene* s, const TraceParams& P, cudaStream_t st) {
+    if (s->scene_class == GLOME_CLASS_FLAT) return launch_trace<false, MODE>(s, P, st);
+    return launch_trace<true, MODE>(s, P, st);
+}
+
+extern "C" int glome_render_dev(GlomeScene* s, const GlomeCamera* cam, int width, int height, const GlomeRenderOpts* o,
+                                double* tcolor_dev, uint32_t* rgb8_dev, GlomeRenderStats* stats, void* stream) {
+    if (!s || !cam || !o || !tcolor_dev || width <= 0 || height <= 0 || o->blocksize <= 0 || o->tile_stride <= 0 ||
+        o->tile_first < 0 || o->tile_first >= o->tile_stride) { g_err = "bad argument"; return GLOME_EINVAL; }
+    CK(cudaSetDevice(s->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    TileGeom g = make_geom(width, height, o->blocksize);
+    int ntiles = g.ntx * g.nty;
+    int n_sel = (ntiles - o->tile_first + o->tile_stride - 1) / o->tile_stride;
+    if (n_sel < 0) n_sel = 0;
+    int launches0 = s->launches;
+    size_t npix = (size_t)width * height;
+    CK(cudaMemsetAsync(s->stats, 0, sizeof(DevStats), st));
+    CK(cudaEventRecord(s->ev0, st));
+    TraceParams P;
+    memset(&P, 0, sizeof(P));
+    P.g = g;
+    P.cam.pos = vec(cam->pos[0], cam->pos[1], cam->pos[2]);
+    P.cam.fwd = vec(cam->fwd[0], cam->fwd[1], cam->fwd[2]);
+    P.cam.up = vec(cam->up[0], cam->up[1], cam->up[2]);
+    P.cam.right = vec(cam->right[0], cam->right[1], cam->right[2]);
+    P.recurs = o->recurs; P.tint = o->tint_depth;
+    P.tile_first = o->tile_first; P.tile_stride = o->tile_stride; P.n_sel = n_sel;
+    P.work_counter = s->work_counter; P.st = s->stats;
+    int rc;
+    if (n_sel > 0) {
+        if (o->mode == GLOME_MODE_ONE_RAY) {
+            P.out = tcolor_dev;
+            if ((rc = launch_trace_c<0>(s, P, st))) return rc;
+        } else {
+            // workspace: v (pass 1-4 samples), ray queue
+            if (s->ws_pix < npix) {
+                cudaFree(s->v); s->v = nullptr; s->ws_pix = 0;
+                CK(cudaMalloc((void**)&s->v, npix * 5 * sizeof(double)));
+                s->ws_pix = npix;
+            }
+            if (s->queue_cap < npix) {
+                cudaFree(s->queue); s->queue = nullptr; s->queue_cap = 0;
+                CK(cudaMalloc((void**)&s->queue, npix * sizeof(int)));
+                s->queue_cap = npix;
+            }
+            DecideParams D;
+            memset(&D, 0, sizeof(D));
+            D.g = g; D.tile_first = o->tile_first; D.tile_stride = o->tile_stride;
+            D.v = s->v; D.v2 = tcolor_dev; D.queue = s->queue; D.queue_count = s->queue_count;
+            P.queue = s->queue; P.queue_count = s->queue_count; P.v = s->v;
+            for (int pass = 1; pass <= 5; pass++) {
+                D.pass = pass;
+                D.threshold = pass >= 2 ? o->thresholds[pass - 2] : 0;
+                CK(cudaMemsetAsync(s->queue_count, 0, sizeof(int), st));
+                k_aa_decide<<<n_sel, 256, 0, st>>>(D);
+                s->launches++;
+                CK(cudaGetLastError());
+                if (pass < 5) { P.out = s->v; if ((rc = launch_trace_c<1>(s, P, st))) return rc; }
+                else { P.out = tcolor_dev; if ((rc = launch_trace_c<5>(s, P, st))) return rc; }
+            }
+        }
+        if (rgb8_dev) {
+            k_pack_rgb8<<<n_sel, 256, 0, st>>>(g, o->tile_first, o->tile_stride, tcolor_dev, rgb8_dev);
+            s->launches++;
+            CK(cudaGetLastError());
+        }
+    }
+    CK(cudaEventRecord(s->ev1, st));
+    if (stats) {
+        CK(cudaEventSynchronize(s->ev1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        read_stats(s, stats, ms, s->launches - launches0);
+    }
+    return GLOME_OK;
+}
+
+extern "C" int glome_render(GlomeScene* s, const GlomeCamera* cam, int width, int height, const GlomeRenderOpts* o,
+                            double* tcolor, uint32_t* rgb8, GlomeRenderStats* stats) {
+    if (!s || !tcolor || width <= 0 || height <= 0) { g_err = "bad argument"; return GLOME_EINVAL; }
+    CK(cudaSetDevice(s->device));
+    size_t npix = (size_t)width * height;
+    if (!s->v2 || s->ws_pix < npix) {
+        cudaFree(s->v2); cudaFree(s->rgb8); cudaFree(s->v);
+        s->v2 = nullptr; s->rgb8 = nullptr; s->v = nullptr; s->ws_pix = 0;
+        CK(cudaMalloc((void**)&s->v2, npix * 5 * sizeof(double)));
+        CK(cudaMalloc((void**)&s->rgb8, npix * sizeof(uint32_t)));
+        CK(cudaMalloc((void**)&s->v, npix * 5 * sizeof(double)));
+        s->ws_pix = npix;
+    }
+    // pixels of unselected tiles must be left untouched: start from the caller's buffer
+    if (o && o->tile_stride > 1) {
+        CK(cudaMemcpy(s->v2, tcolor, npix * 5 * sizeof(double), cudaMemcpyHostToDevice));
+        if (rgb8) CK(cudaMemcpy(s->rgb8, rgb8, npix * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    GlomeRenderStats local;
+    int rc = glome_render_dev(s, cam, width, height, o, s->v2, rgb8 ? s->rgb8 : nullptr, &local, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpy(tcolor, s->v2, npix * 5 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (rgb8) CK(cudaMemcpy(rgb8, s->rgb8, npix * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (stats) *stats = local;
+    return GLOME_OK;
+}
+
+extern "C" int glome_dev_alloc(int device, int64_t bytes, void** out) {
+    if (!out || bytes < 0) { g_err = "bad argument"; return GLOME_EINVAL; }
+    CK(cudaSetDevice(device));
+    CK(cudaMalloc(out, (size_t)(bytes ? bytes : 1)));
+    return GLOME_OK;
+}
+extern "C" int glome_dev_free(int device, void* p) {
+    CK(cudaSetDevice(device));
+    CK(cudaFree(p));
+    return GLOME_OK;
+}
