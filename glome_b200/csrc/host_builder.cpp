@@ -919,6 +919,7 @@ void Builder::flatten_into(int item, int slot, int depth) {
             int nbase = (int)f_bih.size();
             // leaf records {first item node, count}
             std::vector<int32_t> leafoff(T.leaves.size() / 2);
+            if (f_ipool.size() & 1) f_ipool.push_back(0);  // leaf records are read as one 8-byte load
             for (size_t l = 0; l < T.leaves.size() / 2; l++) {
                 leafoff[l] = (int32_t)f_ipool.size();
                 f_ipool.push_back(first + T.leaves[2 * l]);
