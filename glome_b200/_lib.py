@@ -83,7 +83,8 @@ class GlomeRenderOpts(C.Structure):
 class GlomeRenderStats(C.Structure):
     _fields_ = [("rays_primary", C.c_int64), ("rays_shadow", C.c_int64), ("rays_secondary", C.c_int64),
                 ("overflow_rays", C.c_int64), ("perlin_range", C.c_int64), ("kernel_ms", C.c_double),
-                ("launches", C.c_int32), ("reserved", C.c_int32)]
+                ("launches", C.c_int32), ("reserved", C.c_int32), ("visits_bih", C.c_int64), ("tests_prim", C.c_int64),
+                ("visits_bvh", C.c_int64), ("tests_tri", C.c_int64)]
 
 
 assert C.sizeof(GlomeHit) == 144 and C.sizeof(GlomeBihNode) == 32 and C.sizeof(GlomeBvhNode) == 128
@@ -109,6 +110,9 @@ SIGNATURES = {
     "glome_dev_alloc": (C.c_int, [C.c_int, C.c_int64, _P(_vp)]),
     "glome_dev_free": (C.c_int, [C.c_int, _vp]),
     "glome_render_opts_default": (None, [_P(GlomeRenderOpts)]),
+    "glome_tile_slots": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "glome_tiles_pack_dev": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "glome_tiles_unpack_dev": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "glome_tile_count": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "glome_tile_rect": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _ip]),
     "glome_builder_create": (C.c_int, [_P(_vp)]),

@@ -112,14 +112,14 @@ __device__ __forceinline__ uint32_t rgbf(Flt r, Flt g, Flt b) {                 
 }
 
 struct DevStats {  // accumulated with atomics
-    unsigned long long primary, shadow, secondary, overflow, perlin_range;
+    unsigned long long primary, shadow, secondary, overflow, perlin_range, bih, prim, bvh, tri;
 };
 
 __device__ __forceinline__ void flush_counters(DevStats* st, unsigned int primary, const RayCounters& rc, unsigned int ovf) {
     // warp-reduce then one atomic per warp and counter
-    unsigned int vals[5] = {primary, rc.shadow, rc.secondary, ovf, rc.perlin_range};
+    unsigned int vals[9] = {primary, rc.shadow, rc.secondary, ovf, rc.perlin_range, rc.cnt.bih, rc.cnt.prim, rc.cnt.bvh, rc.cnt.tri};
 #pragma unroll
-    for (int k = 0; k < 5; k++) {
+    for (int k = 0; k < 9; k++) {
         unsigned int v = vals[k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -131,6 +131,10 @@ __device__ __forceinline__ void flush_counters(DevStats* st, unsigned int primar
         if (vals[2]) atomicAdd(&st->secondary, (unsigned long long)vals[2]);
         if (vals[3]) atomicAdd(&st->overflow, (unsigned long long)vals[3]);
         if (vals[4]) atomicAdd(&st->perlin_range, (unsigned long long)vals[4]);
+        if (vals[5]) atomicAdd(&st->bih, (unsigned long long)vals[5]);
+        if (vals[6]) atomicAdd(&st->prim, (unsigned long long)vals[6]);
+        if (vals[7]) atomicAdd(&st->bvh, (unsigned long long)vals[7]);
+        if (vals[8]) atomicAdd(&st->tri, (unsigned long long)vals[8]);
     }
 }
 
@@ -188,7 +192,7 @@ __global__ void __launch_bounds__(128) k_trace_batch(DScene S, long long n, cons
                                                      const double* __restrict__ tmax, int stride, int recurs,
                                                      double* __restrict__ rgba, double* __restrict__ depth,
                                                      GlomeHit* __restrict__ hits, DevStats* st) {
-    RayCounters rc = {0, 0, 0};
+    RayCounters rc = {0, 0, 0, {0, 0, 0, 0}};
     unsigned int ovf = 0, prim = 0;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         ColorA c;
@@ -228,7 +232,7 @@ struct TraceParams {
 template <bool GEN, int MODE>
 __global__ void __launch_bounds__(GEN ? 64 : 128) k_trace_samples(DScene S, TraceParams P) {
     const int lane = threadIdx.x & 31;
-    RayCounters rc = {0, 0, 0};
+    RayCounters rc = {0, 0, 0, {0, 0, 0, 0}};
     unsigned int ovf = 0, nprim = 0;
     const long long total = (MODE == 0) ? (long long)P.n_sel * P.g.slots_per_tile : (long long)(*P.queue_count);
     for (;;) {
@@ -600,6 +604,10 @@ static void read_stats(GlomeScene* s, GlomeRenderStats* out, float ms, int launc
     out->kernel_ms = ms;
     out->launches = launches;
     out->reserved = 0;
+    out->visits_bih = (int64_t)h.bih;
+    out->tests_prim = (int64_t)h.prim;
+    out->visits_bvh = (int64_t)h.bvh;
+    out->tests_tri = (int64_t)h.tri;
 }
 
 extern "C" int glome_trace_batch(GlomeScene* s, int64_t n, const double* rays, const double* tmax, int tmax_stride, int recurs,
@@ -755,7 +763,7 @@ extern "C" int glome_render_dev(GlomeScene* s, const GlomeCamera* cam, int width
 
 extern "C" int glome_render(GlomeScene* s, const GlomeCamera* cam, int width, int height, const GlomeRenderOpts* o,
                             double* tcolor, uint32_t* rgb8, GlomeRenderStats* stats) {
-    if (!s || !tcolor || width <= 0 || height <= 0) { g_err = "bad argument"; return GLOME_EINVAL; }
+    if (!s || (!tcolor && !rgb8) || width <= 0 || height <= 0) { g_err = "bad argument"; return GLOME_EINVAL; }
     CK(cudaSetDevice(s->device));
     size_t npix = (size_t)width * height;
     if (!s->v2 || s->ws_pix < npix) {
@@ -768,13 +776,13 @@ extern "C" int glome_render(GlomeScene* s, const GlomeCamera* cam, int width, in
     }
     // pixels of unselected tiles must be left untouched: start from the caller's buffer
     if (o && o->tile_stride > 1) {
-        CK(cudaMemcpy(s->v2, tcolor, npix * 5 * sizeof(double), cudaMemcpyHostToDevice));
+        if (tcolor) CK(cudaMemcpy(s->v2, tcolor, npix * 5 * sizeof(double), cudaMemcpyHostToDevice));
         if (rgb8) CK(cudaMemcpy(s->rgb8, rgb8, npix * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
     GlomeRenderStats local;
     int rc = glome_render_dev(s, cam, width, height, o, s->v2, rgb8 ? s->rgb8 : nullptr, &local, nullptr);
     if (rc) return rc;
-    CK(cudaMemcpy(tcolor, s->v2, npix * 5 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (tcolor) CK(cudaMemcpy(tcolor, s->v2, npix * 5 * sizeof(double), cudaMemcpyDeviceToHost));
     if (rgb8) CK(cudaMemcpy(rgb8, s->rgb8, npix * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     if (stats) *stats = local;
     return GLOME_OK;
@@ -790,4 +798,51 @@ extern "C" int glome_dev_free(int device, void* p) {
     CK(cudaSetDevice(device));
     CK(cudaFree(p));
     return GLOME_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU plumbing: a rank's tiles <-> a contiguous slot buffer (equal-sized all-gather payload)
+// ---------------------------------------------------------------------------------------------
+template <bool PACK>
+__global__ void __launch_bounds__(256) k_tiles_copy(TileGeom g, int tile_first, int tile_stride, int words,
+                                                    uint32_t* __restrict__ frame, uint32_t* __restrict__ packed) {
+    int ti = tile_first + blockIdx.x * tile_stride;
+    if (ti >= g.ntx * g.nty) return;
+    int xt, yt, tw, th;
+    tile_rect(g, ti, xt, yt, tw, th);
+    size_t slot = (size_t)blockIdx.x * g.bs * g.bs * words;
+    int n = tw * th * words;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int p = i / words, wd = i % words;
+        size_t fi = ((size_t)(yt + p / tw) * g.width + (xt + p % tw)) * words + wd;
+        size_t pi = slot + (size_t)p * words + wd;
+        if (PACK) packed[pi] = frame[fi];
+        else frame[fi] = packed[pi];
+    }
+}
+extern "C" int glome_tile_slots(int width, int height, int blocksize, int tile_stride) {
+    int n = glome_tile_count(width, height, blocksize);
+    if (tile_stride <= 0) return 0;
+    return (n + tile_stride - 1) / tile_stride;
+}
+static int tiles_copy(bool pack, int width, int height, int blocksize, int tile_first, int tile_stride, int elem_bytes,
+                      void* frame, void* packed, void* stream) {
+    if (width <= 0 || height <= 0 || blocksize <= 0 || tile_stride <= 0 || tile_first < 0 || elem_bytes <= 0 ||
+        (elem_bytes & 3) || !frame || !packed) { g_err = "bad argument"; return GLOME_EINVAL; }
+    TileGeom g = make_geom(width, height, blocksize);
+    int slots = glome_tile_slots(width, height, blocksize, tile_stride);
+    if (slots == 0) return GLOME_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pack) k_tiles_copy<true><<<slots, 256, 0, st>>>(g, tile_first, tile_stride, elem_bytes / 4, (uint32_t*)frame, (uint32_t*)packed);
+    else k_tiles_copy<false><<<slots, 256, 0, st>>>(g, tile_first, tile_stride, elem_bytes / 4, (uint32_t*)frame, (uint32_t*)packed);
+    CK(cudaGetLastError());
+    return GLOME_OK;
+}
+extern "C" int glome_tiles_pack_dev(int width, int height, int blocksize, int tile_first, int tile_stride, int elem_bytes,
+                                    const void* frame_dev, void* packed_dev, void* stream) {
+    return tiles_copy(true, width, height, blocksize, tile_first, tile_stride, elem_bytes, (void*)frame_dev, packed_dev, stream);
+}
+extern "C" int glome_tiles_unpack_dev(int width, int height, int blocksize, int tile_first, int tile_stride, int elem_bytes,
+                                      const void* packed_dev, void* frame_dev, void* stream) {
+    return tiles_copy(false, width, height, blocksize, tile_first, tile_stride, elem_bytes, frame_dev, (void*)packed_dev, stream);
 }

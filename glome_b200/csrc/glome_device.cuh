@@ -39,6 +39,9 @@ struct DScene {
 #define GDEV_CSG_CAP 48     /* rayint_advance chain cap on the device (flagged, never silent) */
 #define GDEV_BIH_STACK 64   /* traversal stack entries (thread-local memory) */
 
+// traversal visit counters (flat kernels only): they feed the roofline's algorithmic-bytes figure
+struct Cnt { unsigned int bih, prim, bvh, tri; };
+
 struct Stk {
     int n;
     int v[GLOME_MAX_STACK];
@@ -411,9 +414,10 @@ __device__ __forceinline__ bool prim_inside(const DScene& S, const GlomeNode& nd
 // the scene-graph interpreter
 // ---------------------------------------------------------------------------------------------
 template <int L>
-__device__ void rayint_node(const DScene& S, int ni, const Ray& r, Flt d, const Stk& tex, const Stk& tag, int csg, Hit& acc);
+__device__ void rayint_node(const DScene& S, int ni, const Ray& r, Flt d, const Stk& tex, const Stk& tag, int csg, Hit& acc,
+                            Cnt* cnt = nullptr);
 template <int L>
-__device__ bool shadow_node(const DScene& S, int ni, const Ray& r, Flt d, int csg);
+__device__ bool shadow_node(const DScene& S, int ni, const Ray& r, Flt d, int csg, Cnt* cnt = nullptr);
 __device__ bool inside_node(const DScene& S, int ni, const Vec& pt);
 __device__ void metainfo_node(const DScene& S, int ni, const Vec& v, Stk& texs, Stk& tags, int& flags);
 
@@ -429,7 +433,7 @@ struct TravEnt { int ref; Flt near_, far_; };
 // rayint_bih (Bih.hs:332-368), iterative, reference order, best-hit culling
 template <int L>
 __device__ __forceinline__ void rayint_bih(const DScene& S, const GlomeNode& nd, const Ray& r, Flt d, const Stk& tex,
-                                           const Stk& tag, int csg, Hit& acc) {
+                                           const Stk& tag, int csg, Hit& acc, Cnt* cnt = nullptr) {
     Bbox bb = ldbb(S.dpool + nd.b);
     Flt near_, far_;
     bbclip_ub(r, bb, near_, far_);
@@ -454,16 +458,18 @@ __device__ __forceinline__ void rayint_bih(const DScene& S, const GlomeNode& nd,
             for (int i = 0; i < lf.y; i++) {
                 int item = lf.x + i;
                 if (linear) {  // bare spheres: no node record to chase
+                    if (cnt) cnt->prim++;
                     Flt t; Vec pos, n;
                     if (prim_sphere<GEN>(S.dpool + a0 + 4 * (item - j0), r, far_, t, pos, n) && cand_wins(acc, t))
                         take_hit(acc, t, pos, n, r, tex, tag, item, -1);
                 } else {
-                    rayint_node<LI>(S, item, r, far_, tex, tag, csg, acc);
+                    rayint_node<LI>(S, item, r, far_, tex, tag, csg, acc, cnt);
                 }
             }
             pop = true;
         } else {
             // 32-byte node: two 16-byte loads
+            if (cnt) cnt->bih++;
             const double2* np = reinterpret_cast<const double2*>(S.bih + ref);
             double2 sp2 = __ldg(np);
             int4 ii = __ldg(reinterpret_cast<const int4*>(np + 1));
@@ -509,7 +515,8 @@ __device__ __forceinline__ void rayint_bih(const DScene& S, const GlomeNode& nd,
 
 // shadow_bih (Bih.hs:510-544)
 template <int L>
-__device__ __forceinline__ bool shadow_bih(const DScene& S, const GlomeNode& nd, const Ray& r, Flt d, int csg) {
+__device__ __forceinline__ bool shadow_bih(const DScene& S, const GlomeNode& nd, const Ray& r, Flt d, int csg,
+                                           Cnt* cnt = nullptr) {
     Bbox bb = ldbb(S.dpool + nd.b);
     Flt near_, farp;
     bbclip_ub(r, bb, near_, farp);
@@ -531,11 +538,13 @@ __device__ __forceinline__ bool shadow_bih(const DScene& S, const GlomeNode& nd,
             Flt dd = fmin_(d, far_);  // shadow s r (fmin d far)  (Bih.hs:515)
             for (int i = 0; i < lf.y; i++) {
                 if (linear) {
+                    if (cnt) cnt->prim++;
                     if (shadow_sphere(S.dpool + a0 + 4 * (lf.x + i - j0), r, dd)) return true;
-                } else if (shadow_node<LI>(S, lf.x + i, r, dd, csg)) return true;
+                } else if (shadow_node<LI>(S, lf.x + i, r, dd, csg, cnt)) return true;
             }
             pop = true;
         } else {
+            if (cnt) cnt->bih++;
             const double2* np = reinterpret_cast<const double2*>(S.bih + ref);
             double2 sp2 = __ldg(np);
             int4 ii = __ldg(reinterpret_cast<const int4*>(np + 1));
@@ -575,7 +584,7 @@ __device__ __forceinline__ bool shadow_bih(const DScene& S, const GlomeNode& nd,
 // child's result depth; we cull by the best hit so far (a superset of that knowledge) while
 // passing the unculled `far` down exactly as the reference does (Mesh.hs:178-184).
 __device__ __forceinline__ void rayint_mesh(const DScene& S, int ni, const GlomeNode& nd, const Ray& ray, Flt depth,
-                                            const Stk& texs, const Stk& tags, bool full, Hit& acc) {
+                                            const Stk& texs, const Stk& tags, bool full, Hit& acc, Cnt* cnt = nullptr) {
     const GlomeMeshHeader* h = reinterpret_cast<const GlomeMeshHeader*>(S.ipool + nd.a);
     const int bb_off = h->bb_off, verts_off = h->verts_off, norms_off = h->norms_off, tris_off = h->tris_off;
     const int texs_off = h->texs_off, tags_off = h->tags_off;
@@ -591,9 +600,10 @@ __device__ __forceinline__ void rayint_mesh(const DScene& S, int ni, const Glome
         bool pop = false;
         if (ref < 0) {
             int k = ~ref;
-            int cnt = __ldg(S.ipool + k);
-            for (int j = 0; j < cnt; j++) {
+            int ntri = __ldg(S.ipool + k);
+            for (int j = 0; j < ntri; j++) {
                 int ti = __ldg(S.ipool + k + 1 + j);
+                if (cnt) cnt->tri++;
                 const int4* tp = reinterpret_cast<const int4*>(S.ipool + tris_off + 8 * ti);
                 int4 t0 = __ldg(tp), t1 = __ldg(tp + 1);  // {a,b,c,na} {nb,nc,tex,tag}
                 Vec a = ldv(S.dpool + verts_off + 3 * t0.x);
@@ -619,6 +629,7 @@ __device__ __forceinline__ void rayint_mesh(const DScene& S, int ni, const Glome
             pop = true;
         } else {
             // 128-byte node: two boxes + two child refs
+            if (cnt) cnt->bvh++;
             const double2* np = reinterpret_cast<const double2*>(S.bvh + ref);
             double2 l0 = __ldg(np), l1 = __ldg(np + 1), l2 = __ldg(np + 2);
             double2 r0 = __ldg(np + 3), r1 = __ldg(np + 4), r2 = __ldg(np + 5);
@@ -782,7 +793,7 @@ __device__ void rayint_difference(const DScene& S, int ni, const GlomeNode& nd, 
 // class Solid: rayint (Solid.hs:146).  Folds the node's result into acc with `nearest`.
 template <int L>
 __device__ void rayint_node(const DScene& S, int ni, const Ray& r, Flt d, const Stk& tex_in, const Stk& tag_in, int csg,
-                            Hit& acc) {
+                            Hit& acc, Cnt* cnt) {
     constexpr bool GEN = (L < 0);
     Stk tex = tex_in, tag = tag_in;
     GlomeNode nd = S.nodes[ni];
@@ -795,6 +806,7 @@ __device__ void rayint_node(const DScene& S, int ni, const Ray& r, Flt d, const 
     }
     if (is_prim(nd.type)) {
         Flt t; Vec pos, n;
+        if (cnt) cnt->prim++;
         if (prim_rayint<GEN>(S, nd, r, d, t, pos, n) && cand_wins(acc, t)) take_hit(acc, t, pos, n, r, tex, tag, ni, -1);
         return;
     }
@@ -803,15 +815,15 @@ __device__ void rayint_node(const DScene& S, int ni, const Ray& r, Flt d, const 
         case GLOME_ONLYSHADOW: return;  // Solid.hs:354, Tex.hs:89
         case GLOME_BIH:
             if constexpr (GEN) rayint_bih_gen(S, nd, r, d, tex, tag, csg, acc);
-            else if constexpr (L == 0 || L == 1) rayint_bih<L>(S, nd, r, d, tex, tag, csg, acc);
+            else if constexpr (L == 0 || L == 1) rayint_bih<L>(S, nd, r, d, tex, tag, csg, acc, cnt);
             return;
         case GLOME_MESH:
             if constexpr (GEN) rayint_mesh_gen(S, ni, nd, r, d, tex, tag, acc);
-            else if constexpr (L == 0 || L == 1) rayint_mesh(S, ni, nd, r, d, tex, tag, false, acc);
+            else if constexpr (L == 0 || L == 1) rayint_mesh(S, ni, nd, r, d, tex, tag, false, acc, cnt);
             return;
         case GLOME_GROUP:  // Solid.hs:327
             if constexpr (L == 0 || GEN) {
-                for (int i = 0; i < nd.b; i++) rayint_node<(GEN ? -1 : 1)>(S, nd.a + i, r, d, tex, tag, csg, acc);
+                for (int i = 0; i < nd.b; i++) rayint_node<(GEN ? -1 : 1)>(S, nd.a + i, r, d, tex, tag, csg, acc, cnt);
             }
             return;
     }
@@ -878,26 +890,29 @@ __device__ void rayint_node(const DScene& S, int ni, const Ray& r, Flt d, const 
 
 // class Solid: shadow (Solid.hs:162)
 template <int L>
-__device__ bool shadow_node(const DScene& S, int ni, const Ray& r, Flt d, int csg) {
+__device__ bool shadow_node(const DScene& S, int ni, const Ray& r, Flt d, int csg, Cnt* cnt) {
     constexpr bool GEN = (L < 0);
     GlomeNode nd = S.nodes[ni];
     while (nd.type == GLOME_TEX || nd.type == GLOME_TAG || nd.type == GLOME_ONLYSHADOW) {  // Tex.hs:57,69,92
         ni = nd.a;
         nd = S.nodes[ni];
     }
-    if (is_prim(nd.type)) return prim_shadow(S, nd, r, d);
+    if (is_prim(nd.type)) {
+        if (cnt) cnt->prim++;
+        return prim_shadow(S, nd, r, d);
+    }
     switch (nd.type) {
         case GLOME_VOID:
         case GLOME_NOSHADOW:
         case GLOME_MESH: return false;  // Solid.hs:356, Tex.hs:81, Mesh.hs:210
         case GLOME_BIH:
             if constexpr (GEN) return shadow_bih_gen(S, nd, r, d, csg);
-            else if constexpr (L == 0 || L == 1) return shadow_bih<L>(S, nd, r, d, csg);
+            else if constexpr (L == 0 || L == 1) return shadow_bih<L>(S, nd, r, d, csg, cnt);
             return false;
         case GLOME_GROUP:  // Solid.hs:330
             if constexpr (L == 0 || GEN) {
                 for (int i = 0; i < nd.b; i++)
-                    if (shadow_node<(GEN ? -1 : 1)>(S, nd.a + i, r, d, csg)) return true;
+                    if (shadow_node<(GEN ? -1 : 1)>(S, nd.a + i, r, d, csg, cnt)) return true;
             }
             return false;
     }
@@ -1084,17 +1099,17 @@ __device__ __forceinline__ void finalize_flat(const DScene& S, const Ray& r, Hit
 
 // rayint sld ray d [] []
 template <bool GEN>
-__device__ __forceinline__ void rayint_scene(const DScene& S, int sld, const Ray& r, Flt d, Hit& h) {
+__device__ __forceinline__ void rayint_scene(const DScene& S, int sld, const Ray& r, Flt d, Hit& h, Cnt* cnt = nullptr) {
     hit_clear(h);
     Stk e;
     stk_clear(e);
-    if (GEN) rayint_node<-1>(S, sld, r, d, e, e, 0, h);
-    else { rayint_node<0>(S, sld, r, d, e, e, 0, h); finalize_flat(S, r, h); }
+    if (GEN) rayint_node<-1>(S, sld, r, d, e, e, 0, h, nullptr);
+    else { rayint_node<0>(S, sld, r, d, e, e, 0, h, cnt); finalize_flat(S, r, h); }
 }
 template <bool GEN>
-__device__ __forceinline__ bool shadow_scene(const DScene& S, int sld, const Ray& r, Flt d) {
-    if (GEN) return shadow_node<-1>(S, sld, r, d, 0);
-    return shadow_node<0>(S, sld, r, d, 0);
+__device__ __forceinline__ bool shadow_scene(const DScene& S, int sld, const Ray& r, Flt d, Cnt* cnt = nullptr) {
+    if (GEN) return shadow_node<-1>(S, sld, r, d, 0, nullptr);
+    return shadow_node<0>(S, sld, r, d, 0, cnt);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1148,6 +1163,7 @@ __device__ Flt noise(const Vec& p) {  // Texture.hs:92-107
 // ---------------------------------------------------------------------------------------------
 struct RayCounters {  // per-thread, reduced by the caller
     unsigned int shadow, secondary, perlin_range;
+    Cnt cnt;
 };
 #define GDEV_MAX_LIGHTS 8
 struct LightCtx {  // ctxb = [(Color, Vec)] (Shader.hs:65), evaluated on first use like the lazy original
@@ -1187,7 +1203,7 @@ __device__ __forceinline__ void mpreshade(const DScene& S, int lightset, int sce
         bool blocked = llen > Lp->rad;
         if (!blocked && Lp->do_shadow) {
             rc.shadow++;
-            blocked = shadow_scene<GEN>(S, scene, mkray(vscaleadd(ri.pos, ri.norm, GLM_DELTA), ldir), llen - (2 * GLM_DELTA));
+            blocked = shadow_scene<GEN>(S, scene, mkray(vscaleadd(ri.pos, ri.norm, GLM_DELTA), ldir), llen - (2 * GLM_DELTA), &rc.cnt);
         }
         if (blocked) continue;
         Flt fall = 1 / (llen * llen);  // Shader.hs:23
@@ -1344,7 +1360,7 @@ __device__ void trace(const DScene& S, int lightset, int sld, const Ray& ray, Fl
                       RayCounters& rc) {
     outc = mkca(0, 0, 0, 0);
     if (recurs == 0) { hit_clear(ri); return; }
-    rayint_scene<GEN>(S, sld, ray, depth, ri);
+    rayint_scene<GEN>(S, sld, ray, depth, ri, &rc.cnt);
     if (!ri.hit) return;  // mmissshade (Shader.hs:186)
     LightCtx ctxb;
     ctxb.done = 0;

@@ -216,6 +216,12 @@ typedef struct GlomeRenderStats {
     double kernel_ms;       /* device time of the last call, CUDA events              */
     int32_t launches;       /* kernels launched by the last call                      */
     int32_t reserved;
+    /* traversal work actually done (flat-class scenes only; 0 for the general interpreter):
+     * the N_* terms of the algorithmic-bytes formula, SURVEY.md section 8(d) */
+    int64_t visits_bih;     /* BIH branch nodes loaded (32 B each)                    */
+    int64_t tests_prim;     /* primitive records tested (sphere 32 B, ...)            */
+    int64_t visits_bvh;     /* Mesh BVH branch nodes loaded (128 B each)              */
+    int64_t tests_tri;      /* mesh triangles tested (32 B Tri + 72 B vertices)       */
 } GlomeRenderStats;
 
 typedef struct GlomeScene GlomeScene; /* opaque device-resident scene */
@@ -241,7 +247,7 @@ int glome_inside_batch(GlomeScene* s, int64_t n, const double* pts, uint8_t* ins
 int glome_trace_batch(GlomeScene* s, int64_t n, const double* rays, const double* tmax,
                       int tmax_stride, int recurs, double* rgba, double* depth, GlomeHit* hits_or_null);
 /* renderTiles (+ blitTile)  (Glome.hs:379-386, 353-358).  tcolor = w*h*5 doubles (r,g,b,a,depth),
- * row-major; rgb8 = w*h uint32 or NULL.  Pixels of tiles not selected by tile_first/tile_stride are
+ * row-major, or NULL when only the packed image is wanted; rgb8 = w*h uint32 or NULL.  Pixels of tiles not selected by tile_first/tile_stride are
  * left untouched. */
 int glome_render(GlomeScene* s, const GlomeCamera* cam, int width, int height,
                  const GlomeRenderOpts* opts, double* tcolor, uint32_t* rgb8, GlomeRenderStats* stats);
@@ -256,6 +262,16 @@ int glome_dev_alloc(int device, int64_t bytes, void** out);
 int glome_dev_free(int device, void* p);
 
 void glome_render_opts_default(GlomeRenderOpts* o);
+
+/* Multi-GPU plumbing (the reference has none).  Rank r of N renders tiles
+ * i with i % N == r; its tiles are packed into ceil(T/N) equal slots of blocksize^2 elements so
+ * that one all-gather of equal-sized buffers collects the frame; unpack scatters rank r's block
+ * back into a full frame.  elem_bytes = 40 (TColor) or 4 (rgb8).  Device pointers. */
+int glome_tile_slots(int width, int height, int blocksize, int tile_stride);
+int glome_tiles_pack_dev(int width, int height, int blocksize, int tile_first, int tile_stride, int elem_bytes,
+                         const void* frame_dev, void* packed_dev, void* stream);
+int glome_tiles_unpack_dev(int width, int height, int blocksize, int tile_first, int tile_stride, int elem_bytes,
+                           const void* packed_dev, void* frame_dev, void* stream);
 
 /* Tile list helpers (chunk, Glome.hs:371-377): number of tiles and tile i's rect, in the order
  * renderTiles enumerates them (x-major). */
