@@ -311,7 +311,7 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": which,
-                         "kernel": "k_trace_samples<flat, one-ray>", "kernel_ms": kern_ms,
+                         "kernel": "k_bih_traverse<closest> + k_surface + k_bih_traverse<any> + k_shade (one wave)", "kernel_ms": kern_ms,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "visits": {"bih_branch": stl.visits_bih, "sphere_tests": stl.tests_prim},
                          "note": "working set (~96 MB) is L2-resident: see profiles/ for L2 and issue-slot figures"},

@@ -107,6 +107,7 @@ SIGNATURES = {
                                _P(GlomeRenderStats)]),
     "glome_render_dev": (C.c_int, [_vp, _P(GlomeCamera), C.c_int, C.c_int, _P(GlomeRenderOpts), _vp, _vp,
                                    _P(GlomeRenderStats), _vp]),
+    "glome_scene_launches": (C.c_int64, [_vp]),
     "glome_dev_alloc": (C.c_int, [C.c_int, C.c_int64, _P(_vp)]),
     "glome_dev_free": (C.c_int, [C.c_int, _vp]),
     "glome_render_opts_default": (None, [_P(GlomeRenderOpts)]),

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "glome_device.cuh"
+#include "glome_wave.cuh"
 
 using namespace gdev;
 
@@ -398,6 +399,17 @@ struct GlomeScene {
     cudaEvent_t ev0, ev1;
     int launches;
     size_t stack_bytes;
+    // wavefront pipeline (flat scenes)
+    bool use_wave;
+    std::vector<gwave::Seg> segs;
+    std::vector<int> segs_linear;
+    gwave::Seg* segs_dev;
+    size_t wave_cap;           // samples
+    double* w_hit_t; int* w_hit_seg; int* w_hit_item; int* w_hit_sub; int* w_hit_flags;
+    double* w_surf; unsigned int* w_occl; int2* w_squeue; int* w_squeue_count;
+    unsigned int* w_counters;  // one work counter per persistent launch of a frame
+    int w_counter_next;
+    int n_scene_lights;
 };
 
 extern "C" int glome_device_count(void) {
@@ -415,6 +427,52 @@ static int upload(GlomeScene* s, const T* src, size_t n, D* dst) {
     if (n) CK(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
     *dst = (const T*)p;
     return GLOME_OK;
+}
+
+// Top-level segments of a GLOME_CLASS_FLAT scene, in the reference's list-fold order (Solid.hs:327).
+static bool stk_push(gwave::Stk& st, int x) {
+    if (st.n >= GLOME_MAX_STACK) return false;
+    for (int i = st.n; i >= 1; i--) st.v[i] = st.v[i - 1];
+    st.v[0] = x;
+    st.n++;
+    return true;
+}
+static bool build_segments(const GlomeFlatScene* d, std::vector<gwave::Seg>& segs) {
+    segs.clear();
+    gwave::Stk rtex, rtag;
+    memset(&rtex, 0, sizeof(rtex));
+    memset(&rtag, 0, sizeof(rtag));
+    int ni = d->root;
+    GlomeNode nd = d->nodes[ni];
+    gwave::Stk t0 = rtex, g0 = rtag;
+    while (nd.type == GLOME_TEX || nd.type == GLOME_TAG) {
+        if (!(nd.type == GLOME_TEX ? stk_push(t0, nd.b) : stk_push(g0, nd.b))) return false;
+        ni = nd.a;
+        nd = d->nodes[ni];
+    }
+    int first, count;
+    if (nd.type == GLOME_GROUP) { rtex = t0; rtag = g0; first = nd.a; count = nd.b; }
+    else { first = d->root; count = 1; }  // single object: its wrappers are handled as item wrappers
+    for (int i = 0; i < count; i++) {
+        int ci = first + i;
+        GlomeNode c = d->nodes[ci];
+        gwave::Stk ct = rtex, cg = rtag;
+        int cj = ci;
+        while (c.type == GLOME_TEX || c.type == GLOME_TAG) {
+            if (!(c.type == GLOME_TEX ? stk_push(ct, c.b) : stk_push(cg, c.b))) return false;
+            cj = c.a;
+            c = d->nodes[cj];
+        }
+        gwave::Seg sg;
+        memset(&sg, 0, sizeof(sg));
+        if (c.type == GLOME_BIH) { sg.kind = gwave::SEG_BIH; sg.node = cj; sg.count = 1; sg.tex = ct; sg.tag = cg; segs.push_back(sg); }
+        else if (c.type == GLOME_MESH) { sg.kind = gwave::SEG_MESH; sg.node = cj; sg.count = 1; sg.tex = ct; sg.tag = cg; segs.push_back(sg); }
+        else if (c.type == GLOME_VOID || (c.type >= GLOME_SPHERE && c.type <= GLOME_CONE)) {
+            if (!segs.empty() && segs.back().kind == gwave::SEG_PRIMS && segs.back().node + segs.back().count == ci) segs.back().count++;
+            else { sg.kind = gwave::SEG_PRIMS; sg.node = ci; sg.count = 1; sg.tex = rtex; sg.tag = rtag; segs.push_back(sg); }
+        } else return false;
+    }
+    return !segs.empty() && segs.size() <= GW_MAX_SEGS;
 }
 
 static int validate(const GlomeFlatScene* d) {
@@ -496,6 +554,23 @@ extern "C" int glome_scene_create(const GlomeFlatScene* desc, int device, GlomeS
         CK(cudaDeviceSetLimit(cudaLimitStackSize, want));
         s->stack_bytes = want;
     }
+    s->use_wave = false;
+    s->segs_dev = nullptr; s->wave_cap = 0;
+    s->w_hit_t = nullptr; s->w_hit_seg = s->w_hit_item = s->w_hit_sub = s->w_hit_flags = nullptr;
+    s->w_surf = nullptr; s->w_occl = nullptr; s->w_squeue = nullptr; s->w_squeue_count = nullptr; s->w_counters = nullptr;
+    s->w_counter_next = 0;
+    s->n_scene_lights = ls[1];
+    if (s->scene_class == GLOME_CLASS_FLAT && !getenv("GLOME_FLAT_MEGAKERNEL") && build_segments(desc, s->segs) &&
+        ls[0] + ls[1] <= 32) {
+        CK(cudaMalloc((void**)&s->segs_dev, sizeof(gwave::Seg) * s->segs.size()));
+        CK(cudaMemcpy(s->segs_dev, s->segs.data(), sizeof(gwave::Seg) * s->segs.size(), cudaMemcpyHostToDevice));
+        CK(cudaMalloc((void**)&s->w_squeue_count, sizeof(int)));
+        CK(cudaMalloc((void**)&s->w_counters, sizeof(unsigned int) * 1024));
+        for (size_t i = 0; i < s->segs.size(); i++)
+            s->segs_linear.push_back(s->segs[i].kind == gwave::SEG_BIH &&
+                                     (desc->nodes[s->segs[i].node].c & GLOME_BIH_LINEAR_SPHERES) ? 1 : 0);
+        s->use_wave = true;
+    }
     *out = s;
     return GLOME_OK;
 }
@@ -507,6 +582,9 @@ extern "C" int glome_scene_destroy(GlomeScene* s) {
     cudaFree(s->v); cudaFree(s->v2); cudaFree(s->rgb8); cudaFree(s->queue);
     cudaFree(s->queue_count); cudaFree(s->work_counter); cudaFree(s->stats);
     for (int i = 0; i < 4; i++) cudaFree(s->bw[i]);
+    cudaFree(s->segs_dev); cudaFree(s->w_hit_t); cudaFree(s->w_hit_seg); cudaFree(s->w_hit_item); cudaFree(s->w_hit_sub);
+    cudaFree(s->w_hit_flags); cudaFree(s->w_surf); cudaFree(s->w_occl); cudaFree(s->w_squeue); cudaFree(s->w_squeue_count);
+    cudaFree(s->w_counters);
     cudaEventDestroy(s->ev0); cudaEventDestroy(s->ev1);
     delete s;
     return GLOME_OK;
@@ -688,6 +766,89 @@ static int launch_trace_c(GlomeScene* s, const TraceParams& P, cudaStream_t st) 
     return launch_trace<true, MODE>(s, P, st);
 }
 
+static int wave_reserve(GlomeScene* s, size_t samples) {
+    if (s->wave_cap >= samples) return GLOME_OK;
+    cudaFree(s->w_hit_t); cudaFree(s->w_hit_seg); cudaFree(s->w_hit_item); cudaFree(s->w_hit_sub); cudaFree(s->w_hit_flags);
+    cudaFree(s->w_surf); cudaFree(s->w_occl); cudaFree(s->w_squeue);
+    s->wave_cap = 0;
+    int nl = s->n_scene_lights > 0 ? s->n_scene_lights : 1;
+    CK(cudaMalloc((void**)&s->w_hit_t, samples * sizeof(double)));
+    CK(cudaMalloc((void**)&s->w_hit_seg, samples * sizeof(int)));
+    CK(cudaMalloc((void**)&s->w_hit_item, samples * sizeof(int)));
+    CK(cudaMalloc((void**)&s->w_hit_sub, samples * sizeof(int)));
+    CK(cudaMalloc((void**)&s->w_hit_flags, samples * sizeof(int)));
+    CK(cudaMalloc((void**)&s->w_surf, samples * 6 * sizeof(double)));
+    CK(cudaMalloc((void**)&s->w_occl, samples * sizeof(unsigned int)));
+    CK(cudaMalloc((void**)&s->w_squeue, samples * nl * sizeof(int2)));
+    s->wave_cap = samples;
+    return GLOME_OK;
+}
+
+template <typename K>
+static int persistent_grid(GlomeScene* s, K kernel, int threads) {
+    int b = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, threads, 0) != cudaSuccess || b < 1) b = 1;
+    return s->sm_count * b;
+}
+
+// One trace wave over the sample list described by W (mode / queue): K1 per segment, K2a, K1' per segment, K2b.
+static int launch_wave(GlomeScene* s, gwave::WaveParams W, long long max_samples, cudaStream_t st) {
+    using namespace gwave;
+    static int g_bih[4] = {0, 0, 0, 0}, g_bvh = 0;
+    if (!g_bvh) {
+        g_bih[0] = persistent_grid(s, k_bih_traverse<false, false>, 128);
+        g_bih[1] = persistent_grid(s, k_bih_traverse<false, true>, 128);
+        g_bih[2] = persistent_grid(s, k_bih_traverse<true, false>, 128);
+        g_bih[3] = persistent_grid(s, k_bih_traverse<true, true>, 128);
+        g_bvh = persistent_grid(s, k_bvh_closest, 128);
+    }
+    long long blocks = (max_samples + 127) / 128;
+    long long cap = (long long)s->sm_count * 16;
+    int sgrid = (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+    W.hit_t = s->w_hit_t; W.hit_seg = s->w_hit_seg; W.hit_item = s->w_hit_item; W.hit_sub = s->w_hit_sub;
+    W.hit_flags = s->w_hit_flags; W.surf = s->w_surf; W.occl = s->w_occl; W.squeue = s->w_squeue;
+    W.squeue_count = s->w_squeue_count; W.stats = (unsigned long long*)s->stats;
+    CK(cudaMemsetAsync(s->w_squeue_count, 0, sizeof(int), st));
+    for (size_t i = 0; i < s->segs.size(); i++) {
+        const Seg& sg = s->segs[i];
+        if (sg.kind == SEG_BIH) {
+            bool linear = (s->segs_linear[i] != 0);
+            unsigned int* ctr = s->w_counters + (s->w_counter_next++ & 1023);
+            if (linear) k_bih_traverse<false, true><<<g_bih[1], 128, 0, st>>>(s->d, W, (int)i, sg, ctr);
+            else k_bih_traverse<false, false><<<g_bih[0], 128, 0, st>>>(s->d, W, (int)i, sg, ctr);
+        } else if (sg.kind == SEG_MESH) {
+            unsigned int* ctr = s->w_counters + (s->w_counter_next++ & 1023);
+            k_bvh_closest<<<g_bvh, 128, 0, st>>>(s->d, W, (int)i, sg, ctr);
+        } else {
+            k_prims_closest<<<sgrid, 128, 0, st>>>(s->d, W, (int)i, sg);
+        }
+        s->launches++;
+        CK(cudaGetLastError());
+    }
+    k_surface<<<sgrid, 128, 0, st>>>(s->d, W, s->segs_dev);
+    s->launches++;
+    CK(cudaGetLastError());
+    if (s->n_scene_lights > 0) {
+        for (size_t i = 0; i < s->segs.size(); i++) {
+            const Seg& sg = s->segs[i];
+            if (sg.kind == SEG_BIH) {
+                bool linear = (s->segs_linear[i] != 0);
+                unsigned int* ctr = s->w_counters + (s->w_counter_next++ & 1023);
+                if (linear) k_bih_traverse<true, true><<<g_bih[3], 128, 0, st>>>(s->d, W, (int)i, sg, ctr);
+                else k_bih_traverse<true, false><<<g_bih[2], 128, 0, st>>>(s->d, W, (int)i, sg, ctr);
+            } else if (sg.kind == SEG_PRIMS) {
+                k_prims_any<<<sgrid, 128, 0, st>>>(s->d, W, sg);
+            } else continue;  // a Mesh casts no shadows (Mesh.hs:210)
+            s->launches++;
+            CK(cudaGetLastError());
+        }
+    }
+    k_shade<<<sgrid, 128, 0, st>>>(s->d, W, s->segs_dev);
+    s->launches++;
+    CK(cudaGetLastError());
+    return GLOME_OK;
+}
+
 extern "C" int glome_render_dev(GlomeScene* s, const GlomeCamera* cam, int width, int height, const GlomeRenderOpts* o,
                                 double* tcolor_dev, uint32_t* rgb8_dev, GlomeRenderStats* stats, void* stream) {
     if (!s || !cam || !o || !tcolor_dev || width <= 0 || height <= 0 || o->blocksize <= 0 || o->tile_stride <= 0 ||
@@ -713,10 +874,25 @@ extern "C" int glome_render_dev(GlomeScene* s, const GlomeCamera* cam, int width
     P.tile_first = o->tile_first; P.tile_stride = o->tile_stride; P.n_sel = n_sel;
     P.work_counter = s->work_counter; P.st = s->stats;
     int rc;
+    gwave::WaveParams W;
+    memset(&W, 0, sizeof(W));
+    if (s->use_wave && n_sel > 0) {
+        W.g.width = g.width; W.g.height = g.height; W.g.bs = g.bs; W.g.ntx = g.ntx; W.g.nty = g.nty; W.g.nbx = g.nbx;
+        W.g.nby = g.nby; W.g.slots_per_tile = g.slots_per_tile;
+        W.cam = P.cam; W.recurs = o->recurs; W.tint = o->tint_depth;
+        W.tile_first = o->tile_first; W.tile_stride = o->tile_stride; W.n_sel = n_sel;
+        size_t need = (o->mode == GLOME_MODE_ONE_RAY) ? (size_t)n_sel * g.slots_per_tile : npix;
+        if ((rc = wave_reserve(s, need))) return rc;
+        s->w_counter_next = 0;
+        CK(cudaMemsetAsync(s->w_counters, 0, sizeof(unsigned int) * 1024, st));
+    }
     if (n_sel > 0) {
         if (o->mode == GLOME_MODE_ONE_RAY) {
             P.out = tcolor_dev;
-            if ((rc = launch_trace_c<0>(s, P, st))) return rc;
+            if (s->use_wave) {
+                W.mode = 0; W.out = tcolor_dev;
+                if ((rc = launch_wave(s, W, (long long)n_sel * g.slots_per_tile, st))) return rc;
+            } else if ((rc = launch_trace_c<0>(s, P, st))) return rc;
         } else {
             // workspace: v (pass 1-4 samples), ray queue
             if (s->ws_pix < npix) {
@@ -741,7 +917,11 @@ extern "C" int glome_render_dev(GlomeScene* s, const GlomeCamera* cam, int width
                 k_aa_decide<<<n_sel, 256, 0, st>>>(D);
                 s->launches++;
                 CK(cudaGetLastError());
-                if (pass < 5) { P.out = s->v; if ((rc = launch_trace_c<1>(s, P, st))) return rc; }
+                if (s->use_wave) {
+                    W.mode = pass < 5 ? 1 : 5; W.queue = s->queue; W.queue_count = s->queue_count; W.v = s->v;
+                    W.out = pass < 5 ? s->v : tcolor_dev;
+                    if ((rc = launch_wave(s, W, (long long)npix, st))) return rc;
+                } else if (pass < 5) { P.out = s->v; if ((rc = launch_trace_c<1>(s, P, st))) return rc; }
                 else { P.out = tcolor_dev; if ((rc = launch_trace_c<5>(s, P, st))) return rc; }
             }
         }
@@ -787,6 +967,8 @@ extern "C" int glome_render(GlomeScene* s, const GlomeCamera* cam, int width, in
     if (stats) *stats = local;
     return GLOME_OK;
 }
+
+extern "C" int64_t glome_scene_launches(GlomeScene* s) { return s ? (int64_t)s->launches : 0; }
 
 extern "C" int glome_dev_alloc(int device, int64_t bytes, void** out) {
     if (!out || bytes < 0) { g_err = "bad argument"; return GLOME_EINVAL; }

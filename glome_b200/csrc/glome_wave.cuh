@@ -1,0 +1,739 @@
+// glome_wave.cuh -- wavefront pipeline for GLOME_CLASS_FLAT scenes.
+//
+// ncu on the first (megakernel) version showed the limiter of this path is SIMT divergence, not
+// bandwidth: 5.6 of 32 lanes active on average, because a thread walked primary ray -> shadow ray
+// 1 -> shadow ray 2 -> shade in sequence and the lanes of a warp finish their walks at very
+// different times.  Here the frame is a sequence of waves over a sample list:
+//
+//   K1  k_bih_traverse<closest> / k_bvh_closest / k_prims_closest   one launch per top-level
+//       segment of the scene, in the reference's fold order; persistent; A LANE WHOSE RAY HAS
+//       FINISHED IMMEDIATELY PULLS THE NEXT SAMPLE, so warps stay full; while-while loop shape
+//       (all lanes walk branches until every lane sits on a leaf, then all do leaves)
+//   K2a k_surface   position/normal of the winning primitive, light facing tests, shadow-ray
+//       queue built with ballot + popc prefix
+//   K1' k_bih_traverse<any> / k_prims_any over the shadow queue (any-hit, early exit)
+//   K2b k_shade     materialShader on the unoccluded lights, TColor out (+ pass-5 combine)
+//
+// Arithmetic per ray is exactly the megakernel's (same device functions), so results are
+// bit-identical; only the schedule differs.
+#pragma once
+#include "glome_device.cuh"
+
+namespace gwave {
+
+using namespace gdev;
+
+#define GW_MAX_SEGS 32
+enum { SEG_BIH = 0, SEG_MESH = 1, SEG_PRIMS = 2 };
+
+// A top-level segment of a flat scene: a Bih, a Mesh, or a run of loose (wrapped) primitives.
+struct Seg {
+    int kind;
+    int node;        // BIH / MESH node index (after unwrapping); PRIMS: first group child node
+    int count;       // PRIMS: number of consecutive group children
+    int pad;
+    Stk tex, tag;    // stacks at the segment (root + child wrappers), head first
+};
+
+struct TileGeomW {
+    int width, height, bs, ntx, nty, nbx, nby, slots_per_tile;
+};
+
+struct WaveParams {
+    TileGeomW g;
+    DCamera cam;
+    int mode;                // 0: implicit one-ray-per-pixel samples; 1: queue at pixel centre grid (getCoords);
+                             // 5: queue at (x+0.5, y+0.5)
+    int recurs, tint;
+    int tile_first, tile_stride, n_sel;
+    const int* queue;
+    const int* queue_count;
+    // per-sample state
+    double* hit_t;
+    int* hit_seg;
+    int* hit_item;
+    int* hit_sub;
+    int* hit_flags;
+    double* surf;            // pos(3), norm(3) per sample
+    unsigned int* occl;      // bit li = light li is occluded
+    int2* squeue;            // shadow queue {sample, light}
+    int* squeue_count;
+    const double* v;         // AA pass 5 reads
+    double* out;             // TColor frame written by k_shade
+    unsigned long long* stats;  // DevStats as 9 counters
+};
+
+__device__ __forceinline__ long long wave_total(const WaveParams& P) {
+    return (P.mode == 0) ? (long long)P.n_sel * P.g.slots_per_tile : (long long)(*P.queue_count);
+}
+// sample index -> pixel; false for the padding slots of partial tiles
+__device__ __forceinline__ bool sample_pixel(const WaveParams& P, long long s, int& x, int& y) {
+    if (P.mode == 0) {
+        int k = (int)(s / P.g.slots_per_tile), local = (int)(s % P.g.slots_per_tile);
+        int ti = P.tile_first + k * P.tile_stride;
+        int tx = ti / P.g.nty, ty = ti % P.g.nty;
+        int xt = tx * P.g.bs, yt = ty * P.g.bs;
+        int tw = min(P.g.bs, P.g.width - xt), th = min(P.g.bs, P.g.height - yt);
+        int blk = local >> 5, l = local & 31;
+        int px = (blk % P.g.nbx) * 8 + (l & 7), py = (blk / P.g.nbx) * 4 + (l >> 3);
+        x = xt + px; y = yt + py;
+        return px < tw && py < th;
+    }
+    int pix = P.queue[s];
+    x = pix % P.g.width; y = pix / P.g.width;
+    return true;
+}
+__device__ __forceinline__ Ray sample_ray(const WaveParams& P, int x, int y) {
+    Flt xc, yc;
+    if (P.mode == 5) getCoordsf(P.g.width, P.g.height, (Flt)x + 0.5, (Flt)y + 0.5, xc, yc);
+    else getCoordsf(P.g.width, P.g.height, (Flt)x, (Flt)y, xc, yc);
+    return camera_ray(P.cam, xc, yc);
+}
+
+__device__ __forceinline__ void wave_flush(unsigned long long* st, const unsigned int (&vals_in)[9]) {
+    unsigned int vals[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+        unsigned int v = vals_in[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        vals[k] = v;
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 9; k++)
+            if (vals[k]) atomicAdd(st + k, (unsigned long long)vals[k]);
+    }
+}
+// stats slots: 0 primary 1 shadow 2 secondary 3 overflow 4 perlin_range 5 bih 6 prim 7 bvh 8 tri
+
+// shadow-ray of light li for the surface point of sample s (Shader.hs:70-78); same arithmetic as mpreshade
+__device__ __forceinline__ bool light_ray(const DScene& S, const double* surf, int li, Ray& r, Flt& d, Vec& ldir, Flt& llen,
+                                          bool& need_shadow) {
+    const GlomeLight* Lp = S.lights + li;
+    Vec pos = vec(surf[0], surf[1], surf[2]), norm = vec(surf[3], surf[4], surf[5]);
+    Vec lvec = vsub(vec(Lp->pos[0], Lp->pos[1], Lp->pos[2]), pos);
+    if (vdot(lvec, norm) < 0) return false;
+    llen = vlen(lvec);
+    ldir = vscale(lvec, 1 / llen);
+    if (llen > Lp->rad) return false;
+    need_shadow = Lp->do_shadow != 0;
+    r = mkray(vscaleadd(pos, norm, GLM_DELTA), ldir);
+    d = llen - (2 * GLM_DELTA);
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 / K1': persistent BIH traversal with per-lane refill.
+//   ANY = false: closest hit over the sample list (rayint_bih, Bih.hs:332-368)
+//   ANY = true : any hit over the shadow queue   (shadow_bih, Bih.hs:510-544)
+//   LINEAR: every leaf item is a bare sphere with linear payload addressing
+// ---------------------------------------------------------------------------------------------
+#define GW_STACK 48
+
+template <bool ANY, bool LINEAR>
+__global__ void __launch_bounds__(128, 4) k_bih_traverse(DScene S, WaveParams P, int segidx, Seg seg, unsigned int* counter) {
+    const unsigned int FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const GlomeNode bn = S.nodes[seg.node];
+    const Bbox bb = ldbb(S.dpool + bn.b);
+    const int j0 = bn.c >> 4;
+    const int a0 = LINEAR ? S.nodes[j0].a : 0;
+    const long long total = ANY ? (long long)(*P.squeue_count) : wave_total(P);
+
+    TravEnt stack[GW_STACK];
+    int sp = 0, ref = 0;
+    bool active = false, nomore = false;
+    long long s = 0;
+    int light = 0;
+    Ray r = mkray(vec(0, 0, 0), vec(0, 0, 1));
+    Flt drx = 0, dry = 0, drz = 0, near_ = 0, far_ = 0, dmax = 0;
+    Flt best_t = GLM_INFINITY;
+    int best_item = -1, best_seg = -1;
+    bool has = false;
+    unsigned int n_bih = 0, n_prim = 0, n_ovf = 0;
+
+    for (;;) {
+        // ---- refill idle lanes ----
+        unsigned int idle = __ballot_sync(FULL, !active);
+        if (idle && !nomore) {
+            unsigned int base = 0;
+            int cnt = __popc(idle);
+            int leader = __ffs(idle) - 1;
+            if (lane == leader) base = atomicAdd(counter, (unsigned int)cnt);
+            base = __shfl_sync(FULL, base, leader);
+            if ((long long)base + cnt >= total) nomore = true;
+            if (!active) {
+                long long w = (long long)base + __popc(idle & ((1u << lane) - 1));
+                if (w < total) {
+                    bool ok;
+                    if (ANY) {
+                        int2 e = P.squeue[w];
+                        s = e.x; light = e.y;
+                        ok = ((P.occl[s] >> light) & 1u) == 0;  // an earlier segment already occludes it
+                        if (ok) {
+                            Vec ldir; Flt llen; bool ns;
+                            ok = light_ray(S, P.surf + 6 * s, light, r, dmax, ldir, llen, ns);
+                        }
+                    } else {
+                        s = w;
+                        int x, y;
+                        ok = sample_pixel(P, s, x, y);
+                        if (ok) {
+                            r = sample_ray(P, x, y);
+                            dmax = GLM_INFINITY;  // trace ... ray infinity (Glome.hs:33)
+                            if (segidx > 0) {     // continue the fold: best so far from earlier segments
+                                best_seg = P.hit_seg[s];
+                                has = best_seg >= 0;
+                                best_t = has ? P.hit_t[s] : (Flt)GLM_INFINITY;
+                                best_item = -1;
+                            } else { has = false; best_t = GLM_INFINITY; best_item = -1; best_seg = -1; }
+                        }
+                    }
+                    if (ok) {
+                        bbclip_ub(r, bb, near_, far_);
+                        far_ = fmin_(dmax, far_);  // traverse root near (fmin d far)
+                        drx = 1 / r.d.x; dry = 1 / r.d.y; drz = 1 / r.d.z;
+                        ref = bn.a; sp = 0;
+                        active = true;
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(FULL, active) == 0) {
+            if (nomore) break;
+            continue;
+        }
+        // ---- walk branches until this lane sits on a leaf (or is done) ----
+        bool done = false;
+        while (active && !done && ref >= 0) {
+            n_bih++;
+            const double2* np = reinterpret_cast<const double2*>(S.bih + ref);
+            double2 sp2 = __ldg(np);
+            int4 ii = __ldg(reinterpret_cast<const int4*>(np + 1));
+            Flt dr_ = (ii.x == 0) ? drx : ((ii.x == 1) ? dry : drz);
+            Flt o = (ii.x == 0) ? r.o.x : ((ii.x == 1) ? r.o.y : r.o.z);
+            Flt dl = (sp2.x - o) * dr_;
+            Flt dr = (sp2.y - o) * dr_;
+            bool pop = false;
+            if (near_ > far_) pop = true;
+            else {
+                int c1, c2;
+                bool v1, v2;
+                Flt n2, f1;
+                if (dr_ > 0) {
+                    c1 = ii.y; v1 = near_ < dl; f1 = fmin_(dl, far_);
+                    c2 = ii.z; v2 = dr < far_; n2 = fmax_(dr, near_);
+                } else {
+                    c1 = ii.z; v1 = near_ < dr; f1 = fmin_(dr, far_);
+                    c2 = ii.y; v2 = dl < far_; n2 = fmax_(dl, near_);
+                }
+                if (!ANY && v2 && has && n2 > best_t) v2 = false;  // best-hit culling
+                if (v1) {
+                    if (v2) {
+                        if (sp < GW_STACK) { stack[sp].ref = c2; stack[sp].near_ = n2; stack[sp].far_ = far_; sp++; }
+                        else n_ovf = 1;
+                    }
+                    ref = c1; far_ = f1;
+                } else if (v2) {
+                    ref = c2; near_ = n2;
+                } else pop = true;
+            }
+            if (pop) {
+                for (;;) {
+                    if (sp == 0) { done = true; break; }
+                    sp--;
+                    ref = stack[sp].ref; near_ = stack[sp].near_; far_ = stack[sp].far_;
+                    if (ANY || !(has && near_ > best_t)) break;
+                }
+            }
+        }
+        // ---- leaf ----
+        if (active && !done && ref < 0) {
+            int k = ~ref;
+            int2 lf = __ldg(reinterpret_cast<const int2*>(S.ipool + k));
+            Flt dd = ANY ? fmin_(dmax, far_) : far_;  // Bih.hs:515 / :339
+            for (int i = 0; i < lf.y; i++) {
+                int item = lf.x + i;
+                if (LINEAR) {
+                    n_prim++;
+                    const double* sph = S.dpool + a0 + 4 * (item - j0);
+                    if (ANY) {
+                        if (shadow_sphere(sph, r, dd)) { has = true; break; }
+                    } else {
+                        Flt t; Vec pp, nn;
+                        if (prim_sphere<false>(sph, r, dd, t, pp, nn) && (!has || !(best_t < t))) {
+                            has = true; best_t = t; best_item = item; best_seg = segidx;
+                        }
+                    }
+                } else {
+                    // {Tex,Tag}* prim leaf item
+                    int ni = item;
+                    GlomeNode nd = S.nodes[ni];
+                    bool blocked = false;
+                    for (;;) {
+                        if (nd.type == GLOME_TEX || nd.type == GLOME_TAG) { ni = nd.a; nd = S.nodes[ni]; continue; }
+                        if (ANY && nd.type == GLOME_ONLYSHADOW) { ni = nd.a; nd = S.nodes[ni]; continue; }
+                        if (!ANY && nd.type == GLOME_NOSHADOW) { ni = nd.a; nd = S.nodes[ni]; continue; }
+                        if (nd.type == GLOME_NOSHADOW || nd.type == GLOME_ONLYSHADOW) blocked = true;
+                        break;
+                    }
+                    if (blocked || !is_prim(nd.type)) continue;
+                    n_prim++;
+                    if (ANY) {
+                        if (prim_shadow(S, nd, r, dd)) { has = true; break; }
+                    } else {
+                        Flt t; Vec pp, nn;
+                        if (prim_rayint<false>(S, nd, r, dd, t, pp, nn) && (!has || !(best_t < t))) {
+                            has = true; best_t = t; best_item = item; best_seg = segidx;
+                        }
+                    }
+                }
+            }
+            if (ANY && has) done = true;
+            else {
+                for (;;) {
+                    if (sp == 0) { done = true; break; }
+                    sp--;
+                    ref = stack[sp].ref; near_ = stack[sp].near_; far_ = stack[sp].far_;
+                    if (ANY || !(has && near_ > best_t)) break;
+                }
+            }
+        }
+        if (active && done) {
+            if (ANY) {
+                if (has) atomicOr(P.occl + s, 1u << light);
+                has = false;
+            } else {
+                if (segidx == 0 || best_seg == segidx) {
+                    P.hit_t[s] = has ? best_t : (Flt)GLM_INFINITY;
+                    P.hit_seg[s] = has ? best_seg : -1;
+                    P.hit_item[s] = best_item;
+                    P.hit_sub[s] = -1;
+                }
+                if (segidx == 0) P.hit_flags[s] = n_ovf ? GLOME_HITFLAG_STACK_OVERFLOW : 0;
+                else if (n_ovf) P.hit_flags[s] |= GLOME_HITFLAG_STACK_OVERFLOW;
+                n_ovf = 0;
+            }
+            active = false;
+        }
+    }
+    __syncwarp();
+    unsigned int vals[9] = {0, 0, 0, 0, 0, n_bih, n_prim, 0, 0};
+    wave_flush(P.stats, vals);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 for a Mesh segment (rayint_mesh, Mesh.hs:136-198): persistent, per-lane refill.
+// A Mesh casts no shadows (Mesh.hs:210), so there is no any-hit variant.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 3) k_bvh_closest(DScene S, WaveParams P, int segidx, Seg seg, unsigned int* counter) {
+    const unsigned int FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const GlomeNode mn = S.nodes[seg.node];
+    const GlomeMeshHeader* h = reinterpret_cast<const GlomeMeshHeader*>(S.ipool + mn.a);
+    const int verts_off = h->verts_off, tris_off = h->tris_off, root = h->root;
+    const Bbox bb = ldbb(S.dpool + h->bb_off);
+    const long long total = wave_total(P);
+
+    TravEnt stack[GW_STACK];
+    int sp = 0, ref = 0;
+    bool active = false, nomore = false;
+    long long s = 0;
+    Ray r = mkray(vec(0, 0, 0), vec(0, 0, 1));
+    Vec rcp = vec(0, 0, 0);
+    Flt near_ = 0, far_ = 0;
+    const Flt depth = GLM_INFINITY;
+    Flt best_t = GLM_INFINITY;
+    int best_sub = -1, best_seg = -1;
+    bool has = false;
+    unsigned int n_bvh = 0, n_tri = 0, n_ovf = 0;
+
+    for (;;) {
+        unsigned int idle = __ballot_sync(FULL, !active);
+        if (idle && !nomore) {
+            unsigned int base = 0;
+            int cnt = __popc(idle);
+            int leader = __ffs(idle) - 1;
+            if (lane == leader) base = atomicAdd(counter, (unsigned int)cnt);
+            base = __shfl_sync(FULL, base, leader);
+            if ((long long)base + cnt >= total) nomore = true;
+            if (!active) {
+                long long w = (long long)base + __popc(idle & ((1u << lane) - 1));
+                if (w < total) {
+                    s = w;
+                    int x, y;
+                    if (sample_pixel(P, s, x, y)) {
+                        r = sample_ray(P, x, y);
+                        if (segidx > 0) {
+                            best_seg = P.hit_seg[s];
+                            has = best_seg >= 0;
+                            best_t = has ? P.hit_t[s] : (Flt)GLM_INFINITY;
+                        } else { has = false; best_t = GLM_INFINITY; best_seg = -1; }
+                        best_sub = -1;
+                        rcp = vrcp(r.d);
+                        bbclip_ub_rcp(r.o, rcp, bb, near_, far_);
+                        ref = root; sp = 0;
+                        active = true;
+                        // Mesh.hs:140: root reject (the fold's earlier results stay as they are)
+                        if (near_ > far_ || near_ > depth || far_ < 0) {
+                            if (segidx == 0) { P.hit_t[s] = GLM_INFINITY; P.hit_seg[s] = -1; P.hit_item[s] = -1; P.hit_sub[s] = -1; P.hit_flags[s] = 0; }
+                            active = false;
+                        }
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(FULL, active) == 0) {
+            if (nomore) break;
+            continue;
+        }
+        bool done = false;
+        while (active && !done && ref >= 0) {
+            n_bvh++;
+            const double2* np = reinterpret_cast<const double2*>(S.bvh + ref);
+            double2 l0 = __ldg(np), l1 = __ldg(np + 1), l2 = __ldg(np + 2);
+            double2 r0 = __ldg(np + 3), r1 = __ldg(np + 4), r2 = __ldg(np + 5);
+            int2 kids = __ldg(reinterpret_cast<const int2*>(np + 6));
+            Flt lnearp, lfarp, rnearp, rfarp;
+            bbclip_ub_rcp(r.o, rcp, mkbb(vec(l0.x, l0.y, l1.x), vec(l1.y, l2.x, l2.y)), lnearp, lfarp);
+            bbclip_ub_rcp(r.o, rcp, mkbb(vec(r0.x, r0.y, r1.x), vec(r1.y, r2.x, r2.y)), rnearp, rfarp);
+            Flt lnear = hmax(near_, lnearp), lfar = hmin(far_, lfarp);
+            Flt rnear = hmax(near_, rnearp), rfar = hmin(far_, rfarp);
+            Flt best = has ? best_t : (Flt)GLM_INFINITY;
+            int c1, c2;
+            Flt n1, f1, n2, f2;
+            if (lnear < rnear) { c1 = kids.x; n1 = lnear; f1 = lfar; c2 = kids.y; n2 = rnear; f2 = rfar; }
+            else { c1 = kids.y; n1 = rnear; f1 = rfar; c2 = kids.x; n2 = lnear; f2 = lfar; }
+            bool v1 = !(n1 > f1 || n1 > depth || f1 < 0) && !(has && n1 > best);
+            Flt f2c = hmin(f2, best);
+            bool v2 = !(n2 > f2c || n2 > depth || f2c < 0);
+            bool pop = false;
+            if (v1) {
+                if (v2) {
+                    if (sp < GW_STACK) { stack[sp].ref = c2; stack[sp].near_ = n2; stack[sp].far_ = f2; sp++; }
+                    else n_ovf = 1;
+                }
+                ref = c1; near_ = n1; far_ = f1;
+            } else if (v2) {
+                ref = c2; near_ = n2; far_ = f2;
+            } else pop = true;
+            if (pop) {
+                for (;;) {
+                    if (sp == 0) { done = true; break; }
+                    sp--;
+                    ref = stack[sp].ref; near_ = stack[sp].near_; far_ = stack[sp].far_;
+                    Flt fc = hmin(far_, has ? best_t : (Flt)GLM_INFINITY);
+                    if (!(near_ > fc || fc < 0)) break;
+                }
+            }
+        }
+        if (active && !done && ref < 0) {
+            int k = ~ref;
+            int ntri = __ldg(S.ipool + k);
+            for (int j = 0; j < ntri; j++) {
+                int ti = __ldg(S.ipool + k + 1 + j);
+                n_tri++;
+                int4 t0 = __ldg(reinterpret_cast<const int4*>(S.ipool + tris_off + 8 * ti));
+                Vec a = ldv(S.dpool + verts_off + 3 * t0.x);
+                Vec b = ldv(S.dpool + verts_off + 3 * t0.y);
+                Vec c = ldv(S.dpool + verts_off + 3 * t0.z);
+                Flt t; Vec pp, nn;
+                Vec z = vec(0, 0, 0);
+                if (prim_triangle<false>(a, b, c, false, z, z, z, r, far_, t, pp, nn) && (!has || !(best_t < t))) {
+                    has = true; best_t = t; best_sub = ti; best_seg = segidx;
+                }
+            }
+            for (;;) {
+                if (sp == 0) { done = true; break; }
+                sp--;
+                ref = stack[sp].ref; near_ = stack[sp].near_; far_ = stack[sp].far_;
+                Flt fc = hmin(far_, has ? best_t : (Flt)GLM_INFINITY);
+                if (!(near_ > fc || fc < 0)) break;
+            }
+        }
+        if (active && done) {
+            if (segidx == 0 || (best_seg == segidx && best_sub >= 0)) {
+                P.hit_t[s] = has ? best_t : (Flt)GLM_INFINITY;
+                P.hit_seg[s] = has ? best_seg : -1;
+                P.hit_item[s] = seg.node;
+                P.hit_sub[s] = best_sub;
+            }
+            if (segidx == 0) P.hit_flags[s] = n_ovf ? GLOME_HITFLAG_STACK_OVERFLOW : 0;
+            else if (n_ovf) P.hit_flags[s] |= GLOME_HITFLAG_STACK_OVERFLOW;
+            n_ovf = 0;
+            active = false;
+        }
+    }
+    __syncwarp();
+    unsigned int vals[9] = {0, 0, 0, 0, 0, 0, 0, n_bvh, n_tri};
+    wave_flush(P.stats, vals);
+}
+
+// unwrap {Tex,Tag,(NoShadow|OnlyShadow)}* down to the primitive; false if the chain blocks this query
+template <bool ANY>
+__device__ __forceinline__ bool unwrap_prim(const DScene& S, int ni, GlomeNode& nd, int& prim) {
+    nd = S.nodes[ni];
+    for (;;) {
+        if (nd.type == GLOME_TEX || nd.type == GLOME_TAG || nd.type == (ANY ? GLOME_ONLYSHADOW : GLOME_NOSHADOW)) {
+            ni = nd.a; nd = S.nodes[ni];
+            continue;
+        }
+        break;
+    }
+    prim = ni;
+    return is_prim(nd.type);
+}
+
+// K1 for a run of loose primitives (group children that are wrapped primitives), list fold order
+__global__ void __launch_bounds__(128) k_prims_closest(DScene S, WaveParams P, int segidx, Seg seg) {
+    const long long total = wave_total(P);
+    unsigned int n_prim = 0;
+    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < total; s += (long long)gridDim.x * blockDim.x) {
+        int x, y;
+        if (!sample_pixel(P, s, x, y)) continue;
+        Ray r = sample_ray(P, x, y);
+        bool has = false;
+        Flt best_t = GLM_INFINITY;
+        int best_item = -1, best_seg = -1;
+        if (segidx > 0) { best_seg = P.hit_seg[s]; has = best_seg >= 0; best_t = has ? P.hit_t[s] : (Flt)GLM_INFINITY; }
+        for (int i = 0; i < seg.count; i++) {
+            GlomeNode nd;
+            int prim;
+            if (!unwrap_prim<false>(S, seg.node + i, nd, prim)) continue;
+            n_prim++;
+            Flt t; Vec pp, nn;
+            if (prim_rayint<false>(S, nd, r, GLM_INFINITY, t, pp, nn) && (!has || !(best_t < t))) {
+                has = true; best_t = t; best_item = seg.node + i; best_seg = segidx;
+            }
+        }
+        if (segidx == 0 || best_seg == segidx) {
+            P.hit_t[s] = has ? best_t : (Flt)GLM_INFINITY;
+            P.hit_seg[s] = has ? best_seg : -1;
+            P.hit_item[s] = best_item;
+            P.hit_sub[s] = -1;
+        }
+        if (segidx == 0) P.hit_flags[s] = 0;
+    }
+    __syncwarp();
+    unsigned int vals[9] = {0, 0, 0, 0, 0, 0, n_prim, 0, 0};
+    wave_flush(P.stats, vals);
+}
+__global__ void __launch_bounds__(128) k_prims_any(DScene S, WaveParams P, Seg seg) {
+    const long long total = *P.squeue_count;
+    unsigned int n_prim = 0;
+    for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < total; w += (long long)gridDim.x * blockDim.x) {
+        int2 e = P.squeue[w];
+        if ((P.occl[e.x] >> e.y) & 1u) continue;
+        Ray r; Flt d, llen; Vec ldir; bool ns;
+        if (!light_ray(S, P.surf + 6 * (long long)e.x, e.y, r, d, ldir, llen, ns)) continue;
+        for (int i = 0; i < seg.count; i++) {
+            GlomeNode nd;
+            int prim;
+            if (!unwrap_prim<true>(S, seg.node + i, nd, prim)) continue;
+            n_prim++;
+            if (prim_shadow(S, nd, r, d)) { atomicOr(P.occl + e.x, 1u << e.y); break; }
+        }
+    }
+    __syncwarp();
+    unsigned int vals[9] = {0, 0, 0, 0, 0, 0, n_prim, 0, 0};
+    wave_flush(P.stats, vals);
+}
+
+// Rebuild the hit's texture / tag stacks: item wrappers (innermost first), then the segment's.
+__device__ __forceinline__ void rebuild_stacks(const DScene& S, const Seg* segs, int seg, int item, int sub, Stk& tex, Stk& tag,
+                                               int& prim, int& flags) {
+    tex = segs[seg].tex;
+    tag = segs[seg].tag;
+    prim = item;
+    if (segs[seg].kind == SEG_MESH) {
+        const GlomeNode mn = S.nodes[item];
+        const GlomeMeshHeader* h = reinterpret_cast<const GlomeMeshHeader*>(S.ipool + mn.a);
+        const int32_t* T = S.ipool + h->tris_off + 8 * sub;
+        if (T[6] != -1) { Stk t2; if (stk_cons(t2, S.ipool[h->texs_off + T[6]], tex)) flags |= GLOME_HITFLAG_STACK_OVERFLOW; tex = t2; }
+        if (T[7] != -1) { Stk t2; if (stk_cons(t2, S.ipool[h->tags_off + T[7]], tag)) flags |= GLOME_HITFLAG_STACK_OVERFLOW; tag = t2; }
+        return;
+    }
+    int ni = item;
+    GlomeNode nd = S.nodes[ni];
+    while (nd.type == GLOME_TEX || nd.type == GLOME_TAG || nd.type == GLOME_NOSHADOW) {
+        if (nd.type == GLOME_TEX) { Stk t2; if (stk_cons(t2, nd.b, tex)) flags |= GLOME_HITFLAG_STACK_OVERFLOW; tex = t2; }
+        else if (nd.type == GLOME_TAG) { Stk t2; if (stk_cons(t2, nd.b, tag)) flags |= GLOME_HITFLAG_STACK_OVERFLOW; tag = t2; }
+        ni = nd.a;
+        nd = S.nodes[ni];
+    }
+    prim = ni;
+}
+
+// materialise the full Hit of sample s from the wave buffers (same arithmetic as finalize_flat)
+__device__ __forceinline__ void load_hit(const DScene& S, const WaveParams& P, const Seg* segs, long long s, const Ray& r, Hit& h) {
+    hit_clear(h);
+    h.flags = P.hit_flags[s];
+    int seg = P.hit_seg[s];
+    if (seg < 0) return;
+    h.hit = 1;
+    h.t = P.hit_t[s];
+    h.sub = P.hit_sub[s];
+    int fl = 0;
+    rebuild_stacks(S, segs, seg, P.hit_item[s], h.sub, h.tex, h.tag, h.prim, fl);
+    h.flags |= fl;
+    h.ray = r;
+    const double* sf = P.surf + 6 * s;
+    h.pos = vec(sf[0], sf[1], sf[2]);
+    h.norm = vec(sf[3], sf[4], sf[5]);
+}
+
+// K2a: surface point of every hit + shadow-ray queue (mpreshade's per-light tests, Shader.hs:65-80)
+__global__ void __launch_bounds__(128) k_surface(DScene S, WaveParams P, const Seg* __restrict__ segs) {
+    const unsigned int FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const long long total = wave_total(P);
+    const int lfirst = S.lightsets[0], lcnt = S.lightsets[1];
+    unsigned int n_shadow = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long iters = (total + stride - 1) / stride;
+    for (long long it = 0; it < iters; it++) {
+        long long s = it * stride + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+        bool live = false;
+        if (s < total) {
+            int x, y;
+            if (sample_pixel(P, s, x, y)) {
+                int seg = P.hit_seg[s];
+                P.occl[s] = 0;
+                if (seg >= 0) {
+                    Ray r = sample_ray(P, x, y);
+                    Hit h;
+                    hit_clear(h);
+                    h.hit = 1; h.t = P.hit_t[s]; h.sub = P.hit_sub[s];
+                    int fl = 0;
+                    rebuild_stacks(S, segs, seg, P.hit_item[s], h.sub, h.tex, h.tag, h.prim, fl);
+                    if (fl) P.hit_flags[s] |= fl;
+                    finalize_flat(S, r, h);
+                    double* sf = P.surf + 6 * s;
+                    sf[0] = h.pos.x; sf[1] = h.pos.y; sf[2] = h.pos.z;
+                    sf[3] = h.norm.x; sf[4] = h.norm.y; sf[5] = h.norm.z;
+                    live = h.tex.n > 0;  // ctxb is only forced when a texture is shaded (Trace.hs:63)
+                }
+            }
+        }
+        for (int li = 0; li < lcnt; li++) {
+            bool emit = false;
+            if (live) {
+                Ray r; Flt d, llen; Vec ldir; bool ns = false;
+                emit = light_ray(S, P.surf + 6 * s, lfirst + li, r, d, ldir, llen, ns) && ns;
+            }
+            unsigned int m = __ballot_sync(FULL, emit);
+            if (m) {
+                int leader = __ffs(m) - 1;
+                int slot = 0;
+                if (lane == leader) slot = atomicAdd(P.squeue_count, __popc(m));
+                slot = __shfl_sync(FULL, slot, leader);
+                if (emit) { P.squeue[slot + __popc(m & ((1u << lane) - 1))] = make_int2((int)s, lfirst + li); n_shadow++; }
+            }
+        }
+    }
+    __syncwarp();
+    unsigned int vals[9] = {0, n_shadow, 0, 0, 0, 0, 0, 0, 0};
+    wave_flush(P.stats, vals);
+}
+
+struct TCw { Flt r, g, b, a, d; };
+__device__ __forceinline__ TCw ldtc(const double* __restrict__ buf, size_t pix) {
+    const double* p = buf + pix * 5;
+    TCw c; c.r = p[0]; c.g = p[1]; c.b = p[2]; c.a = p[3]; c.d = p[4];
+    return c;
+}
+__device__ __forceinline__ TCw getcw(const double* __restrict__ v, int width, int xt, int yt, int tw, int th, int x, int y) {
+    if ((x >= xt) && (x < xt + tw) && (y >= yt) && (y < yt + th)) return ldtc(v, (size_t)y * width + x);
+    TCw c; c.r = 0; c.g = 0; c.b = 0; c.a = 0; c.d = GLM_INFINITY;
+    return c;
+}
+
+// K2b: trace's texture fold + materialShader for Surface materials (Trace.hs:59-82, Shader.hs:82-105)
+__global__ void __launch_bounds__(128) k_shade(DScene S, WaveParams P, const Seg* __restrict__ segs) {
+    const long long total = wave_total(P);
+    const int lfirst = S.lightsets[0], lcnt = S.lightsets[1];
+    unsigned int n_primary = 0, n_ovf = 0, n_perlin = 0;
+    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < total; s += (long long)gridDim.x * blockDim.x) {
+        int x, y;
+        if (!sample_pixel(P, s, x, y)) continue;
+        n_primary++;
+        Ray ray = sample_ray(P, x, y);
+        Hit ri;
+        load_hit(S, P, segs, s, ray, ri);
+        if (ri.flags) n_ovf++;
+        ColorA colora = mkca(0, 0, 0, 0);
+        if (ri.hit && P.recurs != 0) {
+            LightCtx ctx;
+            ctx.done = 0; ctx.n = 0;
+            RayCounters rc = {0, 0, 0, {0, 0, 0, 0}};
+            Vec eyedir = vinvert(ray.d);
+            for (int i = 0; i < ri.tex.n; i++) {
+                if (colora.a + GLM_DELTA >= 1) continue;  // opaque (Trace.hs:50)
+                if (!ctx.done) {  // mpreshade with the shadow results of K1'
+                    ctx.done = 1;
+                    unsigned int oc = P.occl[s];
+                    for (int li = 0; li < lcnt; li++) {
+                        Ray sr; Flt d, llen; Vec ldir; bool ns;
+                        if (!light_ray(S, P.surf + 6 * s, lfirst + li, sr, d, ldir, llen, ns)) continue;
+                        if (ns && ((oc >> (lfirst + li)) & 1u)) continue;
+                        const GlomeLight* Lp = S.lights + lfirst + li;
+                        Flt fall = 1 / (llen * llen);
+                        if (ctx.n < GDEV_MAX_LIGHTS) {
+                            ctx.col[ctx.n].r = Lp->color[0] * fall;
+                            ctx.col[ctx.n].g = Lp->color[1] * fall;
+                            ctx.col[ctx.n].b = Lp->color[2] * fall;
+                            ctx.dir[ctx.n] = ldir;
+                            ctx.n++;
+                        }
+                    }
+                }
+                MatVal m;
+                eval_texture(S, ri.tex.v[i], ri, m, rc);
+                ColorA colorb;
+                if (m.kind == GLOME_MAT_SURFACE) shade_surface(ctx, m.p, ri.norm, eyedir, colorb);
+                else if (m.kind == GLOME_MAT_BLEND) {
+                    ColorA ca, cb;
+                    shade_surface(ctx, S.materials[m.a].p, ri.norm, eyedir, ca);
+                    shade_surface(ctx, S.materials[m.b].p, ri.norm, eyedir, cb);
+                    colorb = caweight(ca, cb, m.p[0]);
+                } else colorb = mkca(0, 0, 0, 0);
+                colora = cafold(colora, colorb);
+            }
+            n_perlin += rc.perlin_range;
+        }
+        TCw col;
+        col.r = colora.r; col.g = colora.g; col.b = colora.b; col.a = colora.a;
+        col.d = (P.recurs != 0) ? ridepth(ri) : (Flt)GLM_INFINITY;
+        size_t pix = (size_t)y * P.g.width + x;
+        double* o = P.out + pix * 5;
+        if (P.mode == 5) {
+            int tx = x / P.g.bs, ty = y / P.g.bs;
+            int xt = tx * P.g.bs, yt = ty * P.g.bs;
+            int tw = min(P.g.bs, P.g.width - xt), th = min(P.g.bs, P.g.height - yt);
+            TCw a = getcw(P.v, P.g.width, xt, yt, tw, th, x, y), b = getcw(P.v, P.g.width, xt, yt, tw, th, x, y + 1);
+            TCw c = getcw(P.v, P.g.width, xt, yt, tw, th, x + 1, y + 1), d = getcw(P.v, P.g.width, xt, yt, tw, th, x + 1, y);
+            bool lastx = x == xt + tw - 1, lasty = y == yt + th - 1;
+            // pass5_combine (Glome.hs:309-316)
+            TCw q;
+            if (lastx && lasty) q = col;
+            else {
+                TCw m;
+                if (lastx) { m.r = (a.r + b.r) * 0.5; m.g = (a.g + b.g) * 0.5; m.b = (a.b + b.b) * 0.5; m.a = (a.a + b.a) * 0.5; m.d = (a.d + b.d) * 0.5; }
+                else if (lasty) { m.r = (a.r + d.r) * 0.5; m.g = (a.g + d.g) * 0.5; m.b = (a.b + d.b) * 0.5; m.a = (a.a + d.a) * 0.5; m.d = (a.d + d.d) * 0.5; }
+                else { m.r = (a.r + b.r + c.r + d.r) * 0.25; m.g = (a.g + b.g + c.g + d.g) * 0.25; m.b = (a.b + b.b + c.b + d.b) * 0.25;
+                       m.a = (a.a + b.a + c.a + d.a) * 0.25; m.d = (a.d + b.d + c.d + d.d) * 0.25; }
+                q.r = (col.r + m.r) * 0.5; q.g = (col.g + m.g) * 0.5; q.b = (col.b + m.b) * 0.5; q.a = (col.a + m.a) * 0.5; q.d = (col.d + m.d) * 0.5;
+            }
+            col = q;
+        } else if (P.mode == 0 && P.tint) {
+            col.r = col.r + (col.d / 400);  // Glome.hs:174
+        }
+        o[0] = col.r; o[1] = col.g; o[2] = col.b; o[3] = col.a; o[4] = col.d;
+    }
+    __syncwarp();
+    unsigned int vals[9] = {n_primary, 0, 0, n_ovf, n_perlin, 0, 0, 0, 0};
+    wave_flush(P.stats, vals);
+}
+
+}  // namespace gwave

@@ -77,10 +77,11 @@ class ShardedRenderer:
         stream; returns the number of kernels this call launched from libglomecuda."""
         st = L.GlomeRenderStats()
         stream = self._stream()
+        l0 = self.lib.glome_scene_launches(self.scene.h)
         L.check(self.lib.glome_render_dev(self.scene.h, C.byref(self.cam), self.w, self.h, C.byref(self.opts),
                                           C.c_void_p(self.tcolor.data_ptr()), C.c_void_p(self.rgb8.data_ptr()),
                                           C.byref(st) if want_stats else None, C.c_void_p(stream)))
-        launches = (1 if self.opts.mode == L.MODE_ONE_RAY else 10) + 1
+        launches = int(self.lib.glome_scene_launches(self.scene.h) - l0)
         if want_stats:
             self.last_stats = st
         if self.world > 1:

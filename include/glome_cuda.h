@@ -258,6 +258,8 @@ int glome_render(GlomeScene* s, const GlomeCamera* cam, int width, int height,
 int glome_render_dev(GlomeScene* s, const GlomeCamera* cam, int width, int height,
                      const GlomeRenderOpts* opts, double* tcolor_dev, uint32_t* rgb8_dev,
                      GlomeRenderStats* stats, void* stream);
+/* cumulative number of kernels this scene handle has launched (bench.py's gpu_launches) */
+int64_t glome_scene_launches(GlomeScene* s);
 int glome_dev_alloc(int device, int64_t bytes, void** out);
 int glome_dev_free(int device, void* p);
 
