@@ -440,6 +440,7 @@ __device__ __forceinline__ void rayint_bih(const DScene& S, const GlomeNode& nd,
     Flt dirr[3] = {1 / r.d.x, 1 / r.d.y, 1 / r.d.z};
     Flt org[3] = {r.o.x, r.o.y, r.o.z};
     far_ = fmin_(d, far_);  // traverse root near (fmin d far)  (Bih.hs:368)
+    if (near_ < 0) near_ = 0;  // origin clamp: a subtree entirely behind the origin holds no valid hit
     TravEnt stack[GDEV_BIH_STACK];
     int sp = 0;
     int ref = nd.a;
@@ -521,6 +522,7 @@ __device__ __forceinline__ bool shadow_bih(const DScene& S, const GlomeNode& nd,
     Flt near_, farp;
     bbclip_ub(r, bb, near_, farp);
     Flt far_ = fmin_(d, farp);
+    if (near_ < 0) near_ = 0;  // origin clamp (see rayint_bih)
     Flt dirr[3] = {1 / r.d.x, 1 / r.d.y, 1 / r.d.z};
     Flt org[3] = {r.o.x, r.o.y, r.o.z};
     TravEnt stack[GDEV_BIH_STACK];

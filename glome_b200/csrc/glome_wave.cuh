@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(128, 4) k_bih_traverse(DScene S, WaveParams P,
                     if (ok) {
                         bbclip_ub(r, bb, near_, far_);
                         far_ = fmin_(dmax, far_);  // traverse root near (fmin d far)
+                        if (near_ < 0) near_ = 0;  // origin clamp: nothing behind the origin can be hit
                         drx = 1 / r.d.x; dry = 1 / r.d.y; drz = 1 / r.d.z;
                         ref = bn.a; sp = 0;
                         active = true;
