@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_build", "libglomecuda.so")
+LIB_PATH = os.environ.get("GLOME_LIB") or os.path.join(_HERE, "_build", "libglomecuda.so")  # GLOME_LIB: A/B builds
 
 GLOME_MAX_STACK = 8
 

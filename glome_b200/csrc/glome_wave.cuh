@@ -123,6 +123,21 @@ __device__ __forceinline__ bool light_ray(const DScene& S, const double* surf, i
     return true;
 }
 
+// unwrap {Tex,Tag,(NoShadow|OnlyShadow)}* down to the primitive; false if the chain blocks this query
+template <bool ANY>
+__device__ __forceinline__ bool unwrap_prim(const DScene& S, int ni, GlomeNode& nd, int& prim) {
+    nd = S.nodes[ni];
+    for (;;) {
+        if (nd.type == GLOME_TEX || nd.type == GLOME_TAG || nd.type == (ANY ? GLOME_ONLYSHADOW : GLOME_NOSHADOW)) {
+            ni = nd.a; nd = S.nodes[ni];
+            continue;
+        }
+        break;
+    }
+    prim = ni;
+    return is_prim(nd.type);
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1 / K1': persistent BIH traversal with per-lane refill.
 //   ANY = false: closest hit over the sample list (rayint_bih, Bih.hs:332-368)
@@ -130,6 +145,15 @@ __device__ __forceinline__ bool light_ray(const DScene& S, const double* surf, i
 //   LINEAR: every leaf item is a bare sphere with linear payload addressing
 // ---------------------------------------------------------------------------------------------
 #define GW_STACK 48
+#ifndef GW_POLICY
+#define GW_POLICY 0
+#endif
+#ifndef GW_BRANCH_REPS
+#define GW_BRANCH_REPS 2
+#endif
+#ifndef GW_REFILL_MIN
+#define GW_REFILL_MIN 8
+#endif
 
 template <bool ANY, bool LINEAR>
 __global__ void __launch_bounds__(128, 4) k_bih_traverse(DScene S, WaveParams P, int segidx, Seg seg, unsigned int* counter) {
@@ -156,7 +180,9 @@ __global__ void __launch_bounds__(128, 4) k_bih_traverse(DScene S, WaveParams P,
     for (;;) {
         // ---- refill idle lanes ----
         unsigned int idle = __ballot_sync(FULL, !active);
-        if (idle && !nomore) {
+        // refill in batches: ray set-up (camera ray, root clip, three divisions) is ~200 instructions, so it
+        // should run with many lanes at once rather than one lane at a time
+        if (__popc(idle) >= GW_REFILL_MIN && !nomore) {
             unsigned int base = 0;
             int cnt = __popc(idle);
             int leader = __ffs(idle) - 1;
@@ -197,6 +223,12 @@ __global__ void __launch_bounds__(128, 4) k_bih_traverse(DScene S, WaveParams P,
                         drx = 1 / r.d.x; dry = 1 / r.d.y; drz = 1 / r.d.z;
                         ref = bn.a; sp = 0;
                         active = true;
+                        if (ref >= 0 && near_ > far_) {  // Bih.hs:347 at the root: miss
+                            if (!ANY && segidx == 0) {
+                                P.hit_t[s] = GLM_INFINITY; P.hit_seg[s] = -1; P.hit_item[s] = -1; P.hit_sub[s] = -1; P.hit_flags[s] = 0;
+                            }
+                            active = false;
+                        }
                     }
                 }
             }
@@ -205,9 +237,20 @@ __global__ void __launch_bounds__(128, 4) k_bih_traverse(DScene S, WaveParams P,
             if (nomore) break;
             continue;
         }
-        // ---- walk branches until this lane sits on a leaf (or is done) ----
+        // ---- one scheduling round.  GW_POLICY 0: while-while (all lanes walk branches until every
+        // lane sits on a leaf, then all do leaves).  GW_POLICY 1: majority vote (the warp executes the
+        // step kind -- branch or leaf -- that more of its lanes are waiting for). ----
         bool done = false;
+#if GW_POLICY == 1
+        const bool atb = active && ref >= 0;
+        const unsigned int mb = __ballot_sync(FULL, atb);
+        const unsigned int ml = __ballot_sync(FULL, active && ref < 0);
+        const bool do_branch = __popc(mb) >= __popc(ml);
+        for (int rep = 0; rep < GW_BRANCH_REPS && do_branch && active && !done && ref >= 0; rep++) {
+#else
+        const bool do_branch = false;
         while (active && !done && ref >= 0) {
+#endif
             n_bih++;
             const double2* np = reinterpret_cast<const double2*>(S.bih + ref);
             double2 sp2 = __ldg(np);
@@ -216,31 +259,28 @@ __global__ void __launch_bounds__(128, 4) k_bih_traverse(DScene S, WaveParams P,
             Flt o = (ii.x == 0) ? r.o.x : ((ii.x == 1) ? r.o.y : r.o.z);
             Flt dl = (sp2.x - o) * dr_;
             Flt dr = (sp2.y - o) * dr_;
-            bool pop = false;
-            if (near_ > far_) pop = true;
-            else {
-                int c1, c2;
-                bool v1, v2;
-                Flt n2, f1;
-                if (dr_ > 0) {
-                    c1 = ii.y; v1 = near_ < dl; f1 = fmin_(dl, far_);
-                    c2 = ii.z; v2 = dr < far_; n2 = fmax_(dr, near_);
-                } else {
-                    c1 = ii.z; v1 = near_ < dr; f1 = fmin_(dr, far_);
-                    c2 = ii.y; v2 = dl < far_; n2 = fmax_(dl, near_);
-                }
-                if (!ANY && v2 && has && n2 > best_t) v2 = false;  // best-hit culling
-                if (v1) {
-                    if (v2) {
-                        if (sp < GW_STACK) { stack[sp].ref = c2; stack[sp].near_ = n2; stack[sp].far_ = far_; sp++; }
-                        else n_ovf = 1;
-                    }
-                    ref = c1; far_ = f1;
-                } else if (v2) {
-                    ref = c2; near_ = n2;
-                } else pop = true;
+            // (the reference's `near > far -> miss` test, Bih.hs:347, can only fire at the root: children are
+            //  entered with near <= far by construction; the root case is handled when the ray is set up)
+            int c1, c2;
+            bool v1, v2;
+            Flt n2, f1;
+            if (dr_ > 0) {
+                c1 = ii.y; v1 = near_ < dl; f1 = fmin_(dl, far_);
+                c2 = ii.z; v2 = dr < far_; n2 = fmax_(dr, near_);
+            } else {
+                c1 = ii.z; v1 = near_ < dr; f1 = fmin_(dr, far_);
+                c2 = ii.y; v2 = dl < far_; n2 = fmax_(dl, near_);
             }
-            if (pop) {
+            if (!ANY && v2 && has && n2 > best_t) v2 = false;  // best-hit culling
+            if (v1) {
+                if (v2) {
+                    if (sp < GW_STACK) { stack[sp].ref = c2; stack[sp].near_ = n2; stack[sp].far_ = far_; sp++; }
+                    else n_ovf = 1;
+                }
+                ref = c1; far_ = f1;
+            } else if (v2) {
+                ref = c2; near_ = n2;
+            } else {
                 for (;;) {
                     if (sp == 0) { done = true; break; }
                     sp--;
@@ -250,7 +290,7 @@ __global__ void __launch_bounds__(128, 4) k_bih_traverse(DScene S, WaveParams P,
             }
         }
         // ---- leaf ----
-        if (active && !done && ref < 0) {
+        if (!do_branch && active && !done && ref < 0) {
             int k = ~ref;
             int2 lf = __ldg(reinterpret_cast<const int2*>(S.ipool + k));
             Flt dd = ANY ? fmin_(dmax, far_) : far_;  // Bih.hs:515 / :339
@@ -269,17 +309,9 @@ __global__ void __launch_bounds__(128, 4) k_bih_traverse(DScene S, WaveParams P,
                     }
                 } else {
                     // {Tex,Tag}* prim leaf item
-                    int ni = item;
-                    GlomeNode nd = S.nodes[ni];
-                    bool blocked = false;
-                    for (;;) {
-                        if (nd.type == GLOME_TEX || nd.type == GLOME_TAG) { ni = nd.a; nd = S.nodes[ni]; continue; }
-                        if (ANY && nd.type == GLOME_ONLYSHADOW) { ni = nd.a; nd = S.nodes[ni]; continue; }
-                        if (!ANY && nd.type == GLOME_NOSHADOW) { ni = nd.a; nd = S.nodes[ni]; continue; }
-                        if (nd.type == GLOME_NOSHADOW || nd.type == GLOME_ONLYSHADOW) blocked = true;
-                        break;
-                    }
-                    if (blocked || !is_prim(nd.type)) continue;
+                    GlomeNode nd;
+                    int prim;
+                    if (!unwrap_prim<ANY>(S, item, nd, prim)) continue;
                     n_prim++;
                     if (ANY) {
                         if (prim_shadow(S, nd, r, dd)) { has = true; break; }
@@ -469,21 +501,6 @@ __global__ void __launch_bounds__(128, 3) k_bvh_closest(DScene S, WaveParams P, 
     __syncwarp();
     unsigned int vals[9] = {0, 0, 0, 0, 0, 0, 0, n_bvh, n_tri};
     wave_flush(P.stats, vals);
-}
-
-// unwrap {Tex,Tag,(NoShadow|OnlyShadow)}* down to the primitive; false if the chain blocks this query
-template <bool ANY>
-__device__ __forceinline__ bool unwrap_prim(const DScene& S, int ni, GlomeNode& nd, int& prim) {
-    nd = S.nodes[ni];
-    for (;;) {
-        if (nd.type == GLOME_TEX || nd.type == GLOME_TAG || nd.type == (ANY ? GLOME_ONLYSHADOW : GLOME_NOSHADOW)) {
-            ni = nd.a; nd = S.nodes[ni];
-            continue;
-        }
-        break;
-    }
-    prim = ni;
-    return is_prim(nd.type);
 }
 
 // K1 for a run of loose primitives (group children that are wrapped primitives), list fold order

@@ -237,7 +237,7 @@ static int scene_sphere_cloud(Builder& b, int64_t n, uint64_t seed, GlomeCamera*
     b.light(vec(3.0 * half, 4.0 * half, 1.0 * half), 15.0 * k, 15.0 * k, 14.0 * k);
     b.light(vec(-2.0 * half, 3.0 * half, 4.0 * half), 6.0 * k, 7.0 * k, 9.0 * k);
     int root = b.tex(b.bih(xs), t_matte(b, 0.8, 0.7, 0.5));
-    make_camera(vec(2.6 * half, 1.8 * half, 2.2 * half), vec(0, 0, 0), vec(0, 1, 0), 45, cam);
+    make_camera(vec(1.7 * half, 1.2 * half, 1.45 * half), vec(0, 0, 0), vec(0, 1, 0), 45, cam);
     *recurs = 3;
     return root;
 }
@@ -312,7 +312,7 @@ static int scene_heightfield(Builder& b, int64_t ntris, uint64_t seed, GlomeCame
     b.light(vec(150, 400, 120), 1.9e5, 1.8e5, 1.6e5);
     b.light(vec(-220, 300, -80), 0.7e5, 0.8e5, 1.0e5);
     int root = b.group(gl);
-    make_camera(vec(150, 75, 190), vec(0, 5, 0), vec(0, 1, 0), 45, cam);
+    make_camera(vec(70, 52, 105), vec(-10, 0, -20), vec(0, 1, 0), 45, cam);
     *recurs = 3;
     return root;
 }

@@ -1,0 +1,107 @@
+"""Full-size checks (BASELINE.json sizes): the oracle is too slow for whole frames at these sizes, so the
+GPU frame is compared with the oracle on a strided sample of 65x65 tiles, plus size-independent properties."""
+import numpy as np
+import pytest
+
+import glome_b200 as G
+from glome_b200 import _lib as L
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def sample_tiles_equal(gs, osc, cam, w, h, opts, ntiles_sample, tol=1e-6, allow=1e-4):
+    tg, _, st = gs.render(cam, w, h, opts)
+    rects = O.tile_rects(w, h, 65)
+    stride = max(1, len(rects) // ntiles_sample)
+    o2 = G.render_opts(mode=opts.mode, recurs=opts.recurs, tile_first=0, tile_stride=stride)
+    to = np.full((h, w, 5), np.nan)
+    osc.render(cam, w, h, o2, out=to)
+    sel = ~np.isnan(to[..., 0])
+    assert sel.sum() >= 65 * 5
+    d = np.abs(tg[sel] - to[sel])
+    d[:, 4] /= np.maximum(np.abs(to[sel][:, 4]), 1.0)
+    bad = d.max(-1) > tol
+    assert bad.mean() <= allow, "%d of %d sampled pixels differ" % (int(bad.sum()), int(sel.sum()))
+    return tg, st, int(sel.sum())
+
+
+def test_config2_full_size_one_ray():
+    b = G.SceneBuilder()
+    root, cam, rec = b.config_scene(2, 1000000)
+    fs = b.flatten(root)
+    gs, osc = G.Scene(fs), O.OracleScene(fs)
+    opts = G.render_opts(mode=L.MODE_ONE_RAY, recurs=rec)
+    tg, st, n = sample_tiles_equal(gs, osc, cam, 1920, 1080, opts, 12, tol=0.0, allow=0.0)  # no pow in this scene: bit-exact
+    assert st.rays_primary == 1920 * 1080 and st.overflow_rays == 0
+    assert (tg[..., 3] > 0).mean() > 0.5, (tg[..., 3] > 0).mean()  # most camera rays hit the cloud
+    # first-hit ids on a strided sample of camera rays, at full scene size
+    ys, xs = np.mgrid[0:1080:9, 0:1920:9]
+    rays = G.camera_rays(cam, 1920, 1080, xs.ravel(), ys.ravel())
+    g, o = gs.rayint(rays), osc.rayint(rays)
+    assert np.array_equal(g["prim"], o["prim"]) and np.array_equal(g["t"], o["t"])
+    assert np.array_equal(gs.shadow(rays[:4000]), osc.shadow(rays[:4000]))
+
+
+def test_config3_full_size_mesh():
+    b = G.SceneBuilder()
+    root, cam, rec = b.config_scene(3, 2000000)
+    fs = b.flatten(root)
+    assert fs.n_bvhnodes > 500000
+    gs, osc = G.Scene(fs), O.OracleScene(fs)
+    opts = G.render_opts(mode=L.MODE_ONE_RAY, recurs=rec)
+    tg, st, n = sample_tiles_equal(gs, osc, cam, 1920, 1080, opts, 10)
+    assert st.overflow_rays == 0 and st.visits_bvh > 0 and st.tests_tri > 0
+    ys, xs = np.mgrid[0:1080:11, 0:1920:11]
+    rays = G.camera_rays(cam, 1920, 1080, xs.ravel(), ys.ravel())
+    g, o = gs.rayint(rays), osc.rayint(rays)
+    assert np.array_equal(g["prim"], o["prim"]) and np.array_equal(g["sub"], o["sub"]) and np.array_equal(g["t"], o["t"])
+    assert np.array_equal(g["tex"], o["tex"]) and np.array_equal(g["tag"], o["tag"])
+
+
+def test_config5_4k_adaptive_aa():
+    b = G.SceneBuilder()
+    root, cam, rec = b.config_scene(5, 2000000)
+    fs = b.flatten(root)
+    gs, osc = G.Scene(fs), O.OracleScene(fs)
+    opts = G.render_opts(mode=L.MODE_ADAPTIVE_AA, recurs=rec)
+    tg, st, n = sample_tiles_equal(gs, osc, cam, 3840, 2160, opts, 8)
+    npix = 3840 * 2160
+    assert npix / 8.5 <= st.rays_primary <= 2 * npix  # 1/8 .. 2 rays per pixel
+    # tile sharding over 8 "ranks" reassembles the same frame bit for bit
+    acc = np.zeros_like(tg)
+    for r in range(8):
+        gs.render(cam, 3840, 2160, G.render_opts(mode=L.MODE_ADAPTIVE_AA, recurs=rec, tile_first=r, tile_stride=8), out=acc)
+    assert np.array_equal(acc, tg)
+
+
+def test_config1_testscene_720x480():
+    b = G.SceneBuilder()
+    root, cam, rec = b.config_scene(1)
+    fs = b.flatten(root)
+    gs, osc = G.Scene(fs), O.OracleScene(fs)
+    for mode in (L.MODE_ONE_RAY, L.MODE_ADAPTIVE_AA):
+        opts = G.render_opts(mode=mode, recurs=rec)
+        tg, _, st = gs.render(cam, 720, 480, opts)
+        to, _ = osc.render(cam, 720, 480, opts)
+        d = np.abs(tg - to)
+        d[..., 4] /= np.maximum(np.abs(to[..., 4]), 1.0)
+        bad = d.max(-1) > 1e-6
+        assert bad.mean() <= 1e-4, "%d pixels differ" % int(bad.sum())
+        assert st.overflow_rays == 0 and st.perlin_range == 0
+        assert st.rays_secondary > 0 and st.rays_shadow > 0
+
+
+def test_config4_csg_reflection_depth():
+    b = G.SceneBuilder()
+    root, cam, rec = b.config_scene(4, 16)
+    fs = b.flatten(root)
+    gs, osc = G.Scene(fs), O.OracleScene(fs)
+    opts = G.render_opts(mode=L.MODE_ONE_RAY, recurs=rec)
+    tg, _, st = gs.render(cam, 1280, 720, opts)
+    to, _ = osc.render(cam, 1280, 720, opts)
+    d = np.abs(tg - to)
+    d[..., 4] /= np.maximum(np.abs(to[..., 4]), 1.0)
+    bad = d.max(-1) > 1e-6
+    assert bad.mean() <= 1e-4, "%d pixels differ" % int(bad.sum())
+    assert rec == 5 and st.rays_secondary > 0 and st.overflow_rays == 0
