@@ -489,7 +489,7 @@ static int validate(const GlomeFlatScene* d) {
                 bad = n.a < 0 || n.a >= d->n_nodes || n.b < 0 || n.b >= d->n_nodes; break;
             case GLOME_TEX: bad = n.a < 0 || n.a >= d->n_nodes || n.b < 0 || n.b >= d->n_textures; break;
             case GLOME_TAG: case GLOME_NOSHADOW: case GLOME_ONLYSHADOW: bad = n.a < 0 || n.a >= d->n_nodes; break;
-            case GLOME_BIH: bad = n.b < 0 || (long long)n.b + 6 > d->n_dpool || (n.a >= 0 ? n.a >= d->n_bihnodes : ~n.a + 1 >= d->n_ipool); break;
+            case GLOME_BIH: bad = n.b < 0 || (long long)n.b + 6 > d->n_dpool || (n.a >= 0 && n.a >= d->n_bihnodes); break;
             case GLOME_MESH: bad = n.a < 0 || (long long)n.a + 12 > d->n_ipool; break;
             case GLOME_VOID: break;
             default: bad = n.a < 0 || n.a >= d->n_dpool; break;
@@ -796,10 +796,10 @@ static int launch_wave(GlomeScene* s, gwave::WaveParams W, long long max_samples
     using namespace gwave;
     static int g_bih[4] = {0, 0, 0, 0}, g_bvh = 0;
     if (!g_bvh) {
-        g_bih[0] = persistent_grid(s, k_bih_traverse<false, false>, 128);
-        g_bih[1] = persistent_grid(s, k_bih_traverse<false, true>, 128);
-        g_bih[2] = persistent_grid(s, k_bih_traverse<true, false>, 128);
-        g_bih[3] = persistent_grid(s, k_bih_traverse<true, true>, 128);
+        g_bih[0] = persistent_grid(s, k_bih_traverse<false, false>, GW_THREADS);
+        g_bih[1] = persistent_grid(s, k_bih_traverse<false, true>, GW_THREADS);
+        g_bih[2] = persistent_grid(s, k_bih_traverse<true, false>, GW_THREADS);
+        g_bih[3] = persistent_grid(s, k_bih_traverse<true, true>, GW_THREADS);
         g_bvh = persistent_grid(s, k_bvh_closest, 128);
     }
     long long blocks = (max_samples + 127) / 128;
@@ -814,8 +814,8 @@ static int launch_wave(GlomeScene* s, gwave::WaveParams W, long long max_samples
         if (sg.kind == SEG_BIH) {
             bool linear = (s->segs_linear[i] != 0);
             unsigned int* ctr = s->w_counters + (s->w_counter_next++ & 1023);
-            if (linear) k_bih_traverse<false, true><<<g_bih[1], 128, 0, st>>>(s->d, W, (int)i, sg, ctr);
-            else k_bih_traverse<false, false><<<g_bih[0], 128, 0, st>>>(s->d, W, (int)i, sg, ctr);
+            if (linear) k_bih_traverse<false, true><<<g_bih[1], GW_THREADS, 0, st>>>(s->d, W, (int)i, sg, ctr);
+            else k_bih_traverse<false, false><<<g_bih[0], GW_THREADS, 0, st>>>(s->d, W, (int)i, sg, ctr);
         } else if (sg.kind == SEG_MESH) {
             unsigned int* ctr = s->w_counters + (s->w_counter_next++ & 1023);
             k_bvh_closest<<<g_bvh, 128, 0, st>>>(s->d, W, (int)i, sg, ctr);
@@ -834,8 +834,8 @@ static int launch_wave(GlomeScene* s, gwave::WaveParams W, long long max_samples
             if (sg.kind == SEG_BIH) {
                 bool linear = (s->segs_linear[i] != 0);
                 unsigned int* ctr = s->w_counters + (s->w_counter_next++ & 1023);
-                if (linear) k_bih_traverse<true, true><<<g_bih[3], 128, 0, st>>>(s->d, W, (int)i, sg, ctr);
-                else k_bih_traverse<true, false><<<g_bih[2], 128, 0, st>>>(s->d, W, (int)i, sg, ctr);
+                if (linear) k_bih_traverse<true, true><<<g_bih[3], GW_THREADS, 0, st>>>(s->d, W, (int)i, sg, ctr);
+                else k_bih_traverse<true, false><<<g_bih[2], GW_THREADS, 0, st>>>(s->d, W, (int)i, sg, ctr);
             } else if (sg.kind == SEG_PRIMS) {
                 k_prims_any<<<sgrid, 128, 0, st>>>(s->d, W, sg);
             } else continue;  // a Mesh casts no shadows (Mesh.hs:210)

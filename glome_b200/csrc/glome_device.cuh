@@ -454,8 +454,8 @@ __device__ __forceinline__ void rayint_bih(const DScene& S, const GlomeNode& nd,
         bool pop = false;
         if (ref < 0) {
             // BihLeaf s -> rayint s r far t tags: list fold with the clipped far as max distance
-            int k = ~ref;
-            int2 lf = __ldg(reinterpret_cast<const int2*>(S.ipool + k));
+            int2 lf;
+            glome_bih_leaf(ref, S.ipool, &lf.x, &lf.y);
             for (int i = 0; i < lf.y; i++) {
                 int item = lf.x + i;
                 if (linear) {  // bare spheres: no node record to chase
@@ -535,8 +535,8 @@ __device__ __forceinline__ bool shadow_bih(const DScene& S, const GlomeNode& nd,
     for (;;) {
         bool pop = false;
         if (ref < 0) {
-            int k = ~ref;
-            int2 lf = __ldg(reinterpret_cast<const int2*>(S.ipool + k));
+            int2 lf;
+            glome_bih_leaf(ref, S.ipool, &lf.x, &lf.y);
             Flt dd = fmin_(d, far_);  // shadow s r (fmin d far)  (Bih.hs:515)
             for (int i = 0; i < lf.y; i++) {
                 if (linear) {
@@ -950,8 +950,8 @@ __device__ bool shadow_node(const DScene& S, int ni, const Ray& r, Flt d, int cs
 // inside_bih (Bih.hs:550-565): point descent, both sides possible
 __device__ bool inside_bih_rec(const DScene& S, int ref, const Vec& pt) {
     if (ref < 0) {
-        int k = ~ref;
-        int first = S.ipool[k], cnt = S.ipool[k + 1];
+        int first, cnt;
+        glome_bih_leaf(ref, S.ipool, &first, &cnt);
         for (int i = 0; i < cnt; i++)
             if (inside_node(S, first + i, pt)) return true;
         return false;
@@ -1009,8 +1009,9 @@ __device__ void metainfo_list(const DScene& S, int first, int count, const Vec& 
 __device__ void metainfo_bih_rec(const DScene& S, int ref, const Vec& pt, Stk& texs, Stk& tags, int& flags) {
     // Bih.hs:568-577
     if (ref < 0) {
-        int k = ~ref;
-        metainfo_list(S, S.ipool[k], S.ipool[k + 1], pt, texs, tags, flags);
+        int first, cnt;
+        glome_bih_leaf(ref, S.ipool, &first, &cnt);
+        metainfo_list(S, first, cnt, pt, texs, tags, flags);
         return;
     }
     GlomeBihNode n = S.bih[ref];

@@ -151,12 +151,18 @@ __device__ __forceinline__ bool unwrap_prim(const DScene& S, int ni, GlomeNode& 
 #ifndef GW_BRANCH_REPS
 #define GW_BRANCH_REPS 2
 #endif
+#ifndef GW_THREADS
+#define GW_THREADS 128
+#endif
+#ifndef GW_MINBLOCKS
+#define GW_MINBLOCKS 8
+#endif
 #ifndef GW_REFILL_MIN
 #define GW_REFILL_MIN 8
 #endif
 
 template <bool ANY, bool LINEAR>
-__global__ void __launch_bounds__(128, 4) k_bih_traverse(DScene S, WaveParams P, int segidx, Seg seg, unsigned int* counter) {
+__global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScene S, WaveParams P, int segidx, Seg seg, unsigned int* counter) {
     const unsigned int FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const GlomeNode bn = S.nodes[seg.node];
@@ -291,8 +297,8 @@ __global__ void __launch_bounds__(128, 4) k_bih_traverse(DScene S, WaveParams P,
         }
         // ---- leaf ----
         if (!do_branch && active && !done && ref < 0) {
-            int k = ~ref;
-            int2 lf = __ldg(reinterpret_cast<const int2*>(S.ipool + k));
+            int2 lf;
+            glome_bih_leaf(ref, S.ipool, &lf.x, &lf.y);
             Flt dd = ANY ? fmin_(dmax, far_) : far_;  // Bih.hs:515 / :339
             for (int i = 0; i < lf.y; i++) {
                 int item = lf.x + i;

@@ -917,13 +917,17 @@ void Builder::flatten_into(int item, int slot, int depth) {
                 for (int j = 0; j < n; j++) flatten_into(it.kids[T.order[j]], first + j, depth + 1);
             }
             int nbase = (int)f_bih.size();
-            // leaf records {first item node, count}
+            // leaf refs: inline {first item node, count} when they fit, else a record in ipool
             std::vector<int32_t> leafoff(T.leaves.size() / 2);
-            if (f_ipool.size() & 1) f_ipool.push_back(0);  // leaf records are read as one 8-byte load
             for (size_t l = 0; l < T.leaves.size() / 2; l++) {
-                leafoff[l] = (int32_t)f_ipool.size();
-                f_ipool.push_back(first + T.leaves[2 * l]);
-                f_ipool.push_back(T.leaves[2 * l + 1]);
+                int32_t lfirst = first + T.leaves[2 * l], lcount = T.leaves[2 * l + 1];
+                if (lcount <= 6 && lfirst < (1 << 27)) leafoff[l] = ~glome_bih_leaf_ref_inline(lfirst, lcount);
+                else {
+                    if ((int64_t)f_ipool.size() >= (1 << 27)) throw BuildError("flatten: ipool too large for a leaf record");
+                    leafoff[l] = ~glome_bih_leaf_ref_escape((int32_t)f_ipool.size());
+                    f_ipool.push_back(lfirst);
+                    f_ipool.push_back(lcount);
+                }
             }
             auto xlate = [&](int32_t ref) -> int32_t { return ref >= 0 ? ref + nbase : ~leafoff[~ref]; };
             for (size_t k = 0; k < T.nodes.size(); k++) {

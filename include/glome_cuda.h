@@ -72,14 +72,29 @@ enum GlomeNodeType {
                                       j0 (the block's first node) is stored in c >> 4 */
 
 /* BihBranch lsplit rsplit axis l r (Bih.hs:55-57), 32 bytes = two 16-byte loads.
- * Child refs: >= 0 index into bihnodes[]; < 0 leaf, k = ~ref is an ipool offset of
- * {first item node index, item count}; leaf items are contiguous GlomeNode records. */
+ * Child refs: >= 0 index into bihnodes[]; < 0 leaf (BihLeaf [s]), k = ~ref:
+ *   (k & 7) != 7 : inline leaf, item count = k & 7 (0..6), first item node index = k >> 3
+ *   (k & 7) == 7 : large leaf, k >> 3 is an ipool offset of {first item node index, item count}
+ * Leaf items are contiguous GlomeNode records, so a leaf visit needs no extra dependent load. */
 typedef struct GlomeBihNode {
     double lsplit, rsplit;
     int32_t axis;
     int32_t left, right;
     int32_t pad;
 } GlomeBihNode;
+
+#if defined(__CUDACC__)
+#define GLOME_HD __host__ __device__
+#else
+#define GLOME_HD
+#endif
+static inline GLOME_HD void glome_bih_leaf(int32_t ref, const int32_t* ipool, int32_t* first, int32_t* count) {
+    int32_t k = ~ref;
+    if ((k & 7) != 7) { *first = k >> 3; *count = k & 7; }
+    else { *first = ipool[k >> 3]; *count = ipool[(k >> 3) + 1]; }
+}
+static inline int32_t glome_bih_leaf_ref_inline(int32_t first, int32_t count) { return ~((first << 3) | count); }
+static inline int32_t glome_bih_leaf_ref_escape(int32_t ipool_off) { return ~((ipool_off << 3) | 7); }
 
 /* Mesh BVH Branch lbb rbb l r (Mesh.hs:36), 128 bytes.  Child refs: >= 0 index into bvhnodes[];
  * < 0 leaf, k = ~ref is an ipool offset of {count, tri index ...} (mesh-local tri indices). */

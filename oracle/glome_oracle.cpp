@@ -539,9 +539,10 @@ static Rayint bih_traverse(const BihCtx& c, int ref, Flt near_, Flt far_) {
     // Bih.hs:339-366
     const Scene& S = *c.S;
     if (ref < 0) {  // BihLeaf s -> rayint s r far t tags   (max distance is the CLIPPED far)
-        int k = ~ref;
-        tl_stats.bih_leaf_items += S.ipool[k + 1];
-        return rayint_list(S, S.ipool[k], S.ipool[k + 1], *c.r, far_, *c.t, *c.tags, c.csg);
+        int32_t lf, lc;
+        glome_bih_leaf(ref, S.ipool.data(), &lf, &lc);
+        tl_stats.bih_leaf_items += lc;
+        return rayint_list(S, lf, lc, *c.r, far_, *c.t, *c.tags, c.csg);
     }
     const GlomeBihNode& n = S.bih[ref];
     tl_stats.bih_branch++;
@@ -575,9 +576,10 @@ static bool bih_shadow_traverse(const BihCtx& c, int ref, Flt near_, Flt far_) {
     // Bih.hs:515-542
     const Scene& S = *c.S;
     if (ref < 0) {  // shadow s r (fmin d far)
-        int k = ~ref;
-        tl_stats.bih_leaf_items += S.ipool[k + 1];
-        return shadow_list(S, S.ipool[k], S.ipool[k + 1], *c.r, fmin_(c.d, far_), c.csg);
+        int32_t lf, lc;
+        glome_bih_leaf(ref, S.ipool.data(), &lf, &lc);
+        tl_stats.bih_leaf_items += lc;
+        return shadow_list(S, lf, lc, *c.r, fmin_(c.d, far_), c.csg);
     }
     const GlomeBihNode& n = S.bih[ref];
     tl_stats.bih_branch++;
@@ -608,7 +610,7 @@ static bool shadow_bih(const Scene& S, int ni, const Ray& r, Flt d, int csg) {
 }
 static bool bih_inside_traverse(const Scene& S, int ref, const Vec& pt) {
     // Bih.hs:552-561
-    if (ref < 0) { int k = ~ref; return inside_list(S, S.ipool[k], S.ipool[k + 1], pt); }
+    if (ref < 0) { int32_t lf, lc; glome_bih_leaf(ref, S.ipool.data(), &lf, &lc); return inside_list(S, lf, lc, pt); }
     const GlomeBihNode& n = S.bih[ref];
     Flt o = va(pt, n.axis);
     return ((o < n.lsplit) ? bih_inside_traverse(S, n.left, pt) : false) ||
@@ -624,7 +626,7 @@ static bool inside_bih(const Scene& S, int ni, const Vec& pt) {
 static void metainfo_list(const Scene& S, int first, int count, const Vec& v, List& texs, List& tags);
 static void bih_metainfo_traverse(const Scene& S, int ref, const Vec& pt, List& texs, List& tags) {
     // Bih.hs:568-577
-    if (ref < 0) { int k = ~ref; metainfo_list(S, S.ipool[k], S.ipool[k + 1], pt, texs, tags); return; }
+    if (ref < 0) { int32_t lf, lc; glome_bih_leaf(ref, S.ipool.data(), &lf, &lc); metainfo_list(S, lf, lc, pt, texs, tags); return; }
     const GlomeBihNode& n = S.bih[ref];
     Flt o = va(pt, n.axis);
     List lt, lg, rt, rg;
