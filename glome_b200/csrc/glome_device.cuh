@@ -825,7 +825,36 @@ __device__ void rayint_node(const DScene& S, int ni, const Ray& r, Flt d, const 
             return;
         case GLOME_GROUP:  // Solid.hs:327
             if constexpr (L == 0 || GEN) {
-                for (int i = 0; i < nd.b; i++) rayint_node<(GEN ? -1 : 1)>(S, nd.a + i, r, d, tex, tag, csg, acc, cnt);
+                for (int i = 0; i < nd.b; i++) {
+                    if constexpr (GEN) {
+                        // {Tex,Tag}* prim children inline (a 64-box chessboard is 64 calls otherwise)
+                        int cj = nd.a + i;
+                        GlomeNode c = S.nodes[cj];
+                        int ntx = 0, ntg = 0;
+                        while (c.type == GLOME_TEX || c.type == GLOME_TAG || c.type == GLOME_NOSHADOW) {
+                            ntx += (c.type == GLOME_TEX); ntg += (c.type == GLOME_TAG);
+                            cj = c.a; c = S.nodes[cj];
+                        }
+                        if (is_prim(c.type)) {
+                            Flt t; Vec pos, n;
+                            if (prim_rayint<true>(S, c, r, d, t, pos, n) && cand_wins(acc, t)) {
+                                take_hit(acc, t, pos, n, r, tex, tag, cj, -1);
+                                if (ntx | ntg) {  // rebuild the stacks of the winner only
+                                    int wj = nd.a + i;
+                                    GlomeNode w = S.nodes[wj];
+                                    while (w.type == GLOME_TEX || w.type == GLOME_TAG || w.type == GLOME_NOSHADOW) {
+                                        if (w.type == GLOME_TEX) { if (stk_cons(acc.tex, w.b, acc.tex)) acc.flags |= GLOME_HITFLAG_STACK_OVERFLOW; }
+                                        else if (w.type == GLOME_TAG) { if (stk_cons(acc.tag, w.b, acc.tag)) acc.flags |= GLOME_HITFLAG_STACK_OVERFLOW; }
+                                        wj = w.a; w = S.nodes[wj];
+                                    }
+                                }
+                            }
+                            continue;
+                        }
+                        if (c.type == GLOME_VOID) continue;
+                    }
+                    rayint_node<(GEN ? -1 : 1)>(S, nd.a + i, r, d, tex, tag, csg, acc, cnt);
+                }
             }
             return;
     }
@@ -913,8 +942,15 @@ __device__ bool shadow_node(const DScene& S, int ni, const Ray& r, Flt d, int cs
             return false;
         case GLOME_GROUP:  // Solid.hs:330
             if constexpr (L == 0 || GEN) {
-                for (int i = 0; i < nd.b; i++)
+                for (int i = 0; i < nd.b; i++) {
+                    if constexpr (GEN) {
+                        GlomeNode c = S.nodes[nd.a + i];
+                        while (c.type == GLOME_TEX || c.type == GLOME_TAG || c.type == GLOME_ONLYSHADOW) c = S.nodes[c.a];
+                        if (is_prim(c.type)) { if (prim_shadow(S, c, r, d)) return true; continue; }
+                        if (c.type == GLOME_VOID || c.type == GLOME_NOSHADOW || c.type == GLOME_MESH) continue;
+                    }
                     if (shadow_node<(GEN ? -1 : 1)>(S, nd.a + i, r, d, csg, cnt)) return true;
+                }
             }
             return false;
     }
@@ -973,8 +1009,12 @@ __device__ bool inside_node(const DScene& S, int ni, const Vec& pt) {
     if (is_prim(nd.type)) return prim_inside(S, nd, pt);
     switch (nd.type) {
         case GLOME_GROUP:  // Solid.hs:331
-            for (int i = 0; i < nd.b; i++)
+            for (int i = 0; i < nd.b; i++) {
+                GlomeNode c = S.nodes[nd.a + i];
+                while (c.type == GLOME_TEX || c.type == GLOME_TAG || c.type == GLOME_NOSHADOW || c.type == GLOME_ONLYSHADOW) c = S.nodes[c.a];
+                if (is_prim(c.type)) { if (prim_inside(S, c, pt)) return true; continue; }
                 if (inside_node(S, nd.a + i, pt)) return true;
+            }
             return false;
         case GLOME_INSTANCE: return inside_node(S, nd.a, invxfm_point(S.dpool + nd.b, pt));  // Solid.hs:473
         case GLOME_BIH: {

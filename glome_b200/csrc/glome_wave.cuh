@@ -257,7 +257,9 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScen
         const bool do_branch = false;
         while (active && !done && ref >= 0) {
 #endif
+#ifndef GW_NOCOUNT
             n_bih++;
+#endif
             const double2* np = reinterpret_cast<const double2*>(S.bih + ref);
             double2 sp2 = __ldg(np);
             int4 ii = __ldg(reinterpret_cast<const int4*>(np + 1));
@@ -303,7 +305,9 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScen
             for (int i = 0; i < lf.y; i++) {
                 int item = lf.x + i;
                 if (LINEAR) {
+#ifndef GW_NOCOUNT
                     n_prim++;
+#endif
                     const double* sph = S.dpool + a0 + 4 * (item - j0);
                     if (ANY) {
                         if (shadow_sphere(sph, r, dd)) { has = true; break; }
