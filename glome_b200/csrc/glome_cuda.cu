@@ -225,6 +225,7 @@ struct TraceParams {
     const int* queue;                    // MODE 1/5
     const int* queue_count;
     unsigned int* work_counter;          // zeroed before launch
+    int chunk;                           // samples per warp fetch (1..32)
     const double* v;                     // MODE 5 reads
     double* out;                         // MODE 0/1: v ; MODE 5: v2
     DevStats* st;
@@ -236,13 +237,16 @@ __global__ void __launch_bounds__(GEN ? 64 : 128) k_trace_samples(DScene S, Trac
     RayCounters rc = {0, 0, 0, {0, 0, 0, 0}};
     unsigned int ovf = 0, nprim = 0;
     const long long total = (MODE == 0) ? (long long)P.n_sel * P.g.slots_per_tile : (long long)(*P.queue_count);
+    // Rays per warp-chunk.  The general interpreter serialises divergent lanes, so when a wave has too few samples
+    // to fill the machine a full 32-ray chunk only lengthens the critical path: hand out smaller chunks then.
+    const unsigned int chunk = (unsigned int)P.chunk;
     for (;;) {
         unsigned int base = 0;
-        if (lane == 0) base = atomicAdd(P.work_counter, 32u);
+        if (lane == 0) base = atomicAdd(P.work_counter, chunk);
         base = __shfl_sync(0xffffffffu, base, 0);
         if ((long long)base >= total) break;
         long long w = (long long)base + lane;
-        bool valid = w < total;
+        bool valid = w < total && lane < (int)chunk;
         int x = 0, y = 0;
         if (MODE == 0) {
             if (valid) {
@@ -304,6 +308,8 @@ struct DecideParams {
     double* v2;          // pass 5 writes averages into it
     int* queue;
     int* queue_count;    // zeroed before launch
+    const double* spec;  // non-null (passes 1-4): samples at every pixel centre were traced up front, so a
+                         // "trace this pixel" decision is a copy instead of a queue entry
 };
 
 __global__ void __launch_bounds__(256) k_aa_decide(DecideParams P) {
@@ -356,6 +362,10 @@ __global__ void __launch_bounds__(256) k_aa_decide(DecideParams P) {
                 }
             }
         }
+        if (P.spec && P.pass < 5) {
+            if (need) st_tc(P.v, (size_t)y * width + x, ld_tc(P.spec, (size_t)y * width + x));
+            continue;
+        }
         // warp-aggregated compaction
         unsigned int m = __ballot_sync(0xffffffffu, need);
         if (m) {
@@ -392,6 +402,7 @@ struct GlomeScene {
     std::vector<void*> bufs;
     // render workspace (grown on demand)
     double* v; double* v2; uint32_t* rgb8; size_t ws_pix;
+    double* spec; size_t spec_pix;
     int* queue; size_t queue_cap;
     int* queue_count; unsigned int* work_counter; DevStats* stats;
     // batch workspace
@@ -520,6 +531,7 @@ extern "C" int glome_scene_create(const GlomeFlatScene* desc, int device, GlomeS
     s->device = device;
     s->scene_class = desc->scene_class;
     s->v = s->v2 = nullptr; s->rgb8 = nullptr; s->ws_pix = 0; s->queue = nullptr; s->queue_cap = 0;
+    s->spec = nullptr; s->spec_pix = 0;
     for (int i = 0; i < 4; i++) { s->bw[i] = nullptr; s->bw_cap[i] = 0; }
     s->launches = 0;
     cudaDeviceProp prop;
@@ -579,7 +591,7 @@ extern "C" int glome_scene_destroy(GlomeScene* s) {
     if (!s) return GLOME_OK;
     cudaSetDevice(s->device);
     for (void* p : s->bufs) cudaFree(p);
-    cudaFree(s->v); cudaFree(s->v2); cudaFree(s->rgb8); cudaFree(s->queue);
+    cudaFree(s->v); cudaFree(s->v2); cudaFree(s->rgb8); cudaFree(s->queue); cudaFree(s->spec);
     cudaFree(s->queue_count); cudaFree(s->work_counter); cudaFree(s->stats);
     for (int i = 0; i < 4; i++) cudaFree(s->bw[i]);
     cudaFree(s->segs_dev); cudaFree(s->w_hit_t); cudaFree(s->w_hit_seg); cudaFree(s->w_hit_item); cudaFree(s->w_hit_sub);
@@ -755,7 +767,15 @@ static int launch_trace(GlomeScene* s, const TraceParams& P, cudaStream_t st) {
         blocks_per_sm = b > 0 ? b : 1;
     }
     CK(cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned int), st));
-    k_trace_samples<GEN, MODE><<<s->sm_count * blocks_per_sm, threads, 0, st>>>(s->d, P);
+    TraceParams Q = P;
+    Q.chunk = 32;
+    if (GEN) {
+        const char* e = getenv("GLOME_GEN_CHUNK");
+        Q.chunk = e ? atoi(e) : 32;
+        if (Q.chunk < 1) Q.chunk = 1;
+        if (Q.chunk > 32) Q.chunk = 32;
+    }
+    k_trace_samples<GEN, MODE><<<s->sm_count * blocks_per_sm, threads, 0, st>>>(s->d, Q);
     s->launches++;
     CK(cudaGetLastError());
     return GLOME_OK;
@@ -910,6 +930,23 @@ extern "C" int glome_render_dev(GlomeScene* s, const GlomeCamera* cam, int width
             D.g = g; D.tile_first = o->tile_first; D.tile_stride = o->tile_stride;
             D.v = s->v; D.v2 = tcolor_dev; D.queue = s->queue; D.queue_count = s->queue_count;
             P.queue = s->queue; P.queue_count = s->queue_count; P.v = s->v;
+            // General scenes: one wave costs several ms of latency however few rays it holds (the recursive
+            // interpreter is latency-bound per warp), so passes 1-4 are speculated: every pixel centre is traced
+            // once, up front, and the per-pass decisions copy from that buffer.  get_color is a pure function of the
+            // sample position, so the frame is bit-identical to the adaptive schedule; only the ray count differs.
+            const bool speculate = !s->use_wave && !getenv("GLOME_NO_SPECULATE");
+            D.spec = nullptr;
+            if (speculate) {
+                if (s->spec_pix < npix) {
+                    cudaFree(s->spec); s->spec = nullptr; s->spec_pix = 0;
+                    CK(cudaMalloc((void**)&s->spec, npix * 5 * sizeof(double)));
+                    s->spec_pix = npix;
+                }
+                TraceParams P0 = P;
+                P0.out = s->spec; P0.tint = 0;
+                if ((rc = launch_trace_c<0>(s, P0, st))) return rc;
+                D.spec = s->spec;
+            }
             for (int pass = 1; pass <= 5; pass++) {
                 D.pass = pass;
                 D.threshold = pass >= 2 ? o->thresholds[pass - 2] : 0;
@@ -917,6 +954,7 @@ extern "C" int glome_render_dev(GlomeScene* s, const GlomeCamera* cam, int width
                 k_aa_decide<<<n_sel, 256, 0, st>>>(D);
                 s->launches++;
                 CK(cudaGetLastError());
+                if (speculate && pass < 5) continue;
                 if (s->use_wave) {
                     W.mode = pass < 5 ? 1 : 5; W.queue = s->queue; W.queue_count = s->queue_count; W.v = s->v;
                     W.out = pass < 5 ? s->v : tcolor_dev;
