@@ -179,6 +179,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="glome_b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--all-configs", action="store_true",
+                    help="also time the other BASELINE.json configs (printed to stderr as a table; the JSON line is unchanged)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -326,11 +328,58 @@ def main():
                           "not GHC: no Haskell toolchain in this image" % (r["tiles"], r["ntiles"], r["seconds"]),
                 "ref_visits_per_ray": {"bih_branch": r["stats"]["bih_branch"] / max(1, r["rays"]),
                                        "sphere_tests": r["stats"]["node_1"] / max(1, r["rays"])}}
+        if args.all_configs and world == 1:
+            all_configs_table(G, L, not args.no_cpu_baseline)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def all_configs_table(G, L, with_cpu):
+    """The other BASELINE.json configs (parity-test cases, not bench lines): device time per frame on one GPU and,
+    optionally, the oracle on the host cores for the same frame (bounded sample of tiles)."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    rows = [("1 TestScene 720x480, 1 ray/px", 1, 0, 720, 480, L.MODE_ONE_RAY),
+            ("1 TestScene 720x480, adaptive AA", 1, 0, 720, 480, L.MODE_ADAPTIVE_AA),
+            ("2 1M spheres 1920x1080, 1 ray/px", 2, 1000000, 1920, 1080, L.MODE_ONE_RAY),
+            ("2 1M spheres 720x480, adaptive AA", 2, 1000000, 720, 480, L.MODE_ADAPTIVE_AA),
+            ("3 2M-tri mesh 1920x1080, 1 ray/px", 3, 2000000, 1920, 1080, L.MODE_ONE_RAY),
+            ("4 CSG grid 1280x720, recurs 5", 4, 16, 1280, 720, L.MODE_ONE_RAY),
+            ("5 2M-tri mesh 3840x2160, adaptive AA", 5, 2000000, 3840, 2160, L.MODE_ADAPTIVE_AA)]
+    print("%-40s %10s %8s %12s %12s %10s" % ("config", "ms/frame", "fps", "Mrays/frame", "GPU Mrays/s", "CPU Mrays/s"), file=sys.stderr)
+    for name, cfg, n, w, h, mode in rows:
+        b = G.SceneBuilder()
+        root, cam, rec = b.config_scene(cfg, n)
+        fs = b.flatten(root)
+        sc = G.Scene(fs)
+        opts = G.render_opts(mode=mode, recurs=rec)
+        ms = []
+        for i in range(6):
+            tc, _, st = sc.render(cam, w, h, opts)
+            if i >= 2:
+                ms.append(st.kernel_ms)
+        rays = st.rays_primary + st.rays_shadow + st.rays_secondary
+        cpu = ""
+        if with_cpu:
+            import oracle as O
+            osc = O.OracleScene(fs)
+            nt = len(O.tile_rects(w, h, 65))
+            k = min(nt, 48)
+            o2 = G.render_opts(mode=mode, recurs=rec, tile_first=0, tile_stride=max(1, nt // k))
+            frame = np.zeros((h, w, 5))
+            t0 = time.perf_counter()
+            osc.render(cam, w, h, o2, threads=os.cpu_count() or 1, max_tiles=k, out=frame)
+            dt = time.perf_counter() - t0
+            so = osc.stats()
+            cpu = "%.2f" % ((so["rays_primary"] + so["rays_shadow"] + so["rays_secondary"]) / dt / 1e6)
+            osc.close()
+        m = float(np.median(ms))
+        print("%-40s %10.3f %8.1f %12.3f %12.1f %10s" % (name, m, 1000.0 / m, rays / 1e6, rays / (m * 1e-3) / 1e6, cpu),
+              file=sys.stderr)
+        sc.close()
 
 
 if __name__ == "__main__":

@@ -19,6 +19,13 @@
 #include "glome_device.cuh"
 #include "glome_wave.cuh"
 
+#ifndef GEN_THREADS
+#define GEN_THREADS 64
+#endif
+#ifndef GEN_MINBLOCKS
+#define GEN_MINBLOCKS 10
+#endif
+
 using namespace gdev;
 
 // ---------------------------------------------------------------------------------------------
@@ -232,7 +239,7 @@ struct TraceParams {
 };
 
 template <bool GEN, int MODE>
-__global__ void __launch_bounds__(GEN ? 64 : 128) k_trace_samples(DScene S, TraceParams P) {
+__global__ void __launch_bounds__(GEN ? GEN_THREADS : 128, GEN ? GEN_MINBLOCKS : 1) k_trace_samples(DScene S, TraceParams P) {
     const int lane = threadIdx.x & 31;
     RayCounters rc = {0, 0, 0, {0, 0, 0, 0}};
     unsigned int ovf = 0, nprim = 0;
@@ -760,7 +767,7 @@ extern "C" int glome_tile_rect(int width, int height, int blocksize, int i, int3
 template <bool GEN, int MODE>
 static int launch_trace(GlomeScene* s, const TraceParams& P, cudaStream_t st) {
     static int blocks_per_sm = 0;
-    const int threads = GEN ? 64 : 128;
+    const int threads = GEN ? GEN_THREADS : 128;
     if (!blocks_per_sm) {
         int b = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace_samples<GEN, MODE>, threads, 0));

@@ -703,8 +703,11 @@ __device__ void rayint_advance(const DScene& S, int ni, const Ray& r, Flt d, con
 }
 
 __device__ bool inside_isect(const DScene& S, int first, int count, const Vec& pt) {  // Csg.hs:99-101
-    for (int i = 0; i < count; i++)
+    for (int i = 0; i < count; i++) {
+        GlomeNode c = S.nodes[first + i];
+        if (is_prim(c.type)) { if (!prim_inside(S, c, pt)) return false; continue; }  // planes of a polyhedron
         if (!inside_node(S, first + i, pt)) return false;
+    }
     return true;
 }
 
@@ -866,6 +869,32 @@ __device__ void rayint_node(const DScene& S, int ni, const Ray& r, Flt d, const 
                 Vec neworig = invxfm_point(xfm, r.o);
                 Flt lenscale = vlen(newdir);
                 Flt invlenscale = 1 / lenscale;
+                {   // {Tex,Tag}* prim child: no recursion (oak leaves, cone / cylinder constructors)
+                    int cj = nd.a;
+                    GlomeNode c = S.nodes[cj];
+                    int nw = 0;
+                    while (c.type == GLOME_TEX || c.type == GLOME_TAG || c.type == GLOME_NOSHADOW) { nw++; cj = c.a; c = S.nodes[cj]; }
+                    if (is_prim(c.type)) {
+                        Ray ir = mkray(neworig, vscale(newdir, invlenscale));
+                        Flt t; Vec pos, n;
+                        if (prim_rayint<true>(S, c, ir, d * lenscale, t, pos, n)) {
+                            Flt tw = t * invlenscale;
+                            if (cand_wins(acc, tw)) {
+                                take_hit(acc, tw, xfm_point(xfm, pos), vnorm(invxfm_norm(xfm, n)), ir, tex, tag, cj, -1);
+                                if (nw) {
+                                    int wj = nd.a;
+                                    GlomeNode w = S.nodes[wj];
+                                    while (w.type == GLOME_TEX || w.type == GLOME_TAG || w.type == GLOME_NOSHADOW) {
+                                        if (w.type == GLOME_TEX) { if (stk_cons(acc.tex, w.b, acc.tex)) acc.flags |= GLOME_HITFLAG_STACK_OVERFLOW; }
+                                        else if (w.type == GLOME_TAG) { if (stk_cons(acc.tag, w.b, acc.tag)) acc.flags |= GLOME_HITFLAG_STACK_OVERFLOW; }
+                                        wj = w.a; w = S.nodes[wj];
+                                    }
+                                }
+                            }
+                        }
+                        return;
+                    }
+                }
                 Hit h;
                 hit_clear(h);
                 rayint_node<-1>(S, nd.a, mkray(neworig, vscale(newdir, invlenscale)), d * lenscale, tex, tag, csg, h);
@@ -962,6 +991,11 @@ __device__ bool shadow_node(const DScene& S, int ni, const Ray& r, Flt d, int cs
                 Vec neworig = invxfm_point(xfm, r.o);
                 Flt lenscale = vlen(newdir);
                 Flt invlenscale = 1 / lenscale;
+                {
+                    GlomeNode c = S.nodes[nd.a];
+                    while (c.type == GLOME_TEX || c.type == GLOME_TAG || c.type == GLOME_ONLYSHADOW) c = S.nodes[c.a];
+                    if (is_prim(c.type)) return prim_shadow(S, c, mkray(neworig, vscale(newdir, invlenscale)), d * lenscale);
+                }
                 return shadow_node<-1>(S, nd.a, mkray(neworig, vscale(newdir, invlenscale)), d * lenscale, csg);
             }
             case GLOME_DIFFERENCE:
@@ -1016,7 +1050,13 @@ __device__ bool inside_node(const DScene& S, int ni, const Vec& pt) {
                 if (inside_node(S, nd.a + i, pt)) return true;
             }
             return false;
-        case GLOME_INSTANCE: return inside_node(S, nd.a, invxfm_point(S.dpool + nd.b, pt));  // Solid.hs:473
+        case GLOME_INSTANCE: {  // Solid.hs:473
+            Vec q = invxfm_point(S.dpool + nd.b, pt);
+            GlomeNode c = S.nodes[nd.a];
+            while (c.type == GLOME_TEX || c.type == GLOME_TAG || c.type == GLOME_NOSHADOW || c.type == GLOME_ONLYSHADOW) c = S.nodes[c.a];
+            if (is_prim(c.type)) return prim_inside(S, c, q);
+            return inside_node(S, nd.a, q);
+        }
         case GLOME_BIH: {
             const double* b = S.dpool + nd.b;
             return (pt.x > b[0]) && (pt.x < b[3]) && (pt.y > b[1]) && (pt.y < b[4]) && (pt.z > b[2]) && (pt.z < b[5]) &&
