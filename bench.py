@@ -205,7 +205,8 @@ def main():
 
     b, fs, cam, recurs = build_scene(G)
     scene = G.Scene(fs, local_rank)
-    rdr = ShardedRenderer(scene, cam, WIDTH, HEIGHT, L.MODE_ONE_RAY, recurs, rank=rank, world=world, want_tcolor=True)
+    # N > 1: the gathered framebuffer is the packed 0x00RRGGBB image (what blitTile writes, Glome.hs:353-358)
+    rdr = ShardedRenderer(scene, cam, WIDTH, HEIGHT, L.MODE_ONE_RAY, recurs, rank=rank, world=world, want_tcolor=False)
     flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.int32, device="cuda")
 
     def barrier():

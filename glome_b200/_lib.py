@@ -114,6 +114,7 @@ SIGNATURES = {
     "glome_tile_slots": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "glome_tiles_pack_dev": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "glome_tiles_unpack_dev": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "glome_tiles_unpack_all_dev": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "glome_tile_count": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "glome_tile_rect": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _ip]),
     "glome_builder_create": (C.c_int, [_P(_vp)]),

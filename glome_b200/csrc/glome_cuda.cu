@@ -1030,14 +1030,19 @@ extern "C" int glome_dev_free(int device, void* p) {
 // ---------------------------------------------------------------------------------------------
 // multi-GPU plumbing: a rank's tiles <-> a contiguous slot buffer (equal-sized all-gather payload)
 // ---------------------------------------------------------------------------------------------
+// blockIdx.x = slot, blockIdx.y = rank offset (unpack of a whole gathered buffer: rank r's block holds the tiles
+// r, r+stride, ...; skip_rank's own tiles are already in place)
 template <bool PACK>
 __global__ void __launch_bounds__(256) k_tiles_copy(TileGeom g, int tile_first, int tile_stride, int words,
-                                                    uint32_t* __restrict__ frame, uint32_t* __restrict__ packed) {
-    int ti = tile_first + blockIdx.x * tile_stride;
+                                                    uint32_t* __restrict__ frame, uint32_t* __restrict__ packed,
+                                                    int slots, int skip_rank) {
+    int rank = tile_first + blockIdx.y;
+    if (rank == skip_rank) return;
+    int ti = rank + blockIdx.x * tile_stride;
     if (ti >= g.ntx * g.nty) return;
     int xt, yt, tw, th;
     tile_rect(g, ti, xt, yt, tw, th);
-    size_t slot = (size_t)blockIdx.x * g.bs * g.bs * words;
+    size_t slot = ((size_t)blockIdx.y * slots + blockIdx.x) * g.bs * g.bs * words;
     int n = tw * th * words;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         int p = i / words, wd = i % words;
@@ -1060,8 +1065,8 @@ static int tiles_copy(bool pack, int width, int height, int blocksize, int tile_
     int slots = glome_tile_slots(width, height, blocksize, tile_stride);
     if (slots == 0) return GLOME_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if (pack) k_tiles_copy<true><<<slots, 256, 0, st>>>(g, tile_first, tile_stride, elem_bytes / 4, (uint32_t*)frame, (uint32_t*)packed);
-    else k_tiles_copy<false><<<slots, 256, 0, st>>>(g, tile_first, tile_stride, elem_bytes / 4, (uint32_t*)frame, (uint32_t*)packed);
+    if (pack) k_tiles_copy<true><<<slots, 256, 0, st>>>(g, tile_first, tile_stride, elem_bytes / 4, (uint32_t*)frame, (uint32_t*)packed, slots, -1);
+    else k_tiles_copy<false><<<slots, 256, 0, st>>>(g, tile_first, tile_stride, elem_bytes / 4, (uint32_t*)frame, (uint32_t*)packed, slots, -1);
     CK(cudaGetLastError());
     return GLOME_OK;
 }
@@ -1072,4 +1077,19 @@ extern "C" int glome_tiles_pack_dev(int width, int height, int blocksize, int ti
 extern "C" int glome_tiles_unpack_dev(int width, int height, int blocksize, int tile_first, int tile_stride, int elem_bytes,
                                       const void* packed_dev, void* frame_dev, void* stream) {
     return tiles_copy(false, width, height, blocksize, tile_first, tile_stride, elem_bytes, frame_dev, (void*)packed_dev, stream);
+}
+
+// Scatter a whole all-gathered buffer (tile_stride rank blocks of `slots` slots each) into the frame in one launch.
+extern "C" int glome_tiles_unpack_all_dev(int width, int height, int blocksize, int tile_stride, int skip_rank, int elem_bytes,
+                                          const void* gathered_dev, void* frame_dev, void* stream) {
+    if (width <= 0 || height <= 0 || blocksize <= 0 || tile_stride <= 0 || elem_bytes <= 0 || (elem_bytes & 3) || !gathered_dev ||
+        !frame_dev) { g_err = "bad argument"; return GLOME_EINVAL; }
+    TileGeom g = make_geom(width, height, blocksize);
+    int slots = glome_tile_slots(width, height, blocksize, tile_stride);
+    if (slots == 0) return GLOME_OK;
+    dim3 grid(slots, tile_stride);
+    k_tiles_copy<false><<<grid, 256, 0, (cudaStream_t)stream>>>(g, 0, tile_stride, elem_bytes / 4, (uint32_t*)frame_dev,
+                                                               (uint32_t*)gathered_dev, slots, skip_rank);
+    CK(cudaGetLastError());
+    return GLOME_OK;
 }

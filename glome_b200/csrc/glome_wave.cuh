@@ -269,26 +269,24 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScen
             Flt dr = (sp2.y - o) * dr_;
             // (the reference's `near > far -> miss` test, Bih.hs:347, can only fire at the root: children are
             //  entered with near <= far by construction; the root case is handled when the ray is set up)
-            int c1, c2;
-            bool v1, v2;
-            Flt n2, f1;
-            if (dr_ > 0) {
-                c1 = ii.y; v1 = near_ < dl; f1 = fmin_(dl, far_);
-                c2 = ii.z; v2 = dr < far_; n2 = fmax_(dr, near_);
-            } else {
-                c1 = ii.z; v1 = near_ < dr; f1 = fmin_(dr, far_);
-                c2 = ii.y; v2 = dl < far_; n2 = fmax_(dl, near_);
-            }
+            // branch-free form of Bih.hs:350-366: the near child is the left one iff dirr > 0
+            const bool fwd = dr_ > 0;
+            const Flt dn = fwd ? dl : dr;   // plane bounding the near child
+            const Flt df = fwd ? dr : dl;   // plane bounding the far child
+            const int c1 = fwd ? ii.y : ii.z;
+            const int c2 = fwd ? ii.z : ii.y;
+            const bool v1 = near_ < dn;
+            const Flt f1 = fmin_(dn, far_);
+            bool v2 = df < far_;
+            const Flt n2 = fmax_(df, near_);
             if (!ANY && v2 && has && n2 > best_t) v2 = false;  // best-hit culling
-            if (v1) {
-                if (v2) {
-                    if (sp < GW_STACK) { stack[sp].ref = c2; stack[sp].near_ = n2; stack[sp].far_ = far_; sp++; }
-                    else n_ovf = 1;
-                }
-                ref = c1; far_ = f1;
-            } else if (v2) {
-                ref = c2; near_ = n2;
-            } else {
+            if (v1 && v2) {
+                if (sp < GW_STACK) { stack[sp].ref = c2; stack[sp].near_ = n2; stack[sp].far_ = far_; sp++; }
+                else n_ovf = 1;
+            }
+            if (v1) { ref = c1; far_ = f1; }
+            else if (v2) { ref = c2; near_ = n2; }
+            else {
                 for (;;) {
                     if (sp == 0) { done = true; break; }
                     sp--;

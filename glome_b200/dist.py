@@ -93,14 +93,10 @@ class ShardedRenderer:
                                                       C.c_void_p(frame.data_ptr()), C.c_void_p(pk.data_ptr()),
                                                       C.c_void_p(stream)))
                 self.dist.all_gather_into_tensor(ga, pk)
-                per = pk.numel()
-                for r in range(self.world):
-                    if r == self.rank:
-                        continue
-                    L.check(self.lib.glome_tiles_unpack_dev(self.w, self.h, self.bs, r, self.world, eb,
-                                                            C.c_void_p(ga.data_ptr() + r * per * ga.element_size()),
-                                                            C.c_void_p(frame.data_ptr()), C.c_void_p(stream)))
-                launches += self.world
+                L.check(self.lib.glome_tiles_unpack_all_dev(self.w, self.h, self.bs, self.world, self.rank, eb,
+                                                            C.c_void_p(ga.data_ptr()), C.c_void_p(frame.data_ptr()),
+                                                            C.c_void_p(stream)))
+                launches += 2
         self.launches += launches
         return launches
 

@@ -289,6 +289,10 @@ int glome_tiles_pack_dev(int width, int height, int blocksize, int tile_first, i
                          const void* frame_dev, void* packed_dev, void* stream);
 int glome_tiles_unpack_dev(int width, int height, int blocksize, int tile_first, int tile_stride, int elem_bytes,
                            const void* packed_dev, void* frame_dev, void* stream);
+/* the whole all-gathered buffer (tile_stride blocks of glome_tile_slots slots) in one launch; skip_rank's block
+ * (already in place) is skipped, -1 = none */
+int glome_tiles_unpack_all_dev(int width, int height, int blocksize, int tile_stride, int skip_rank, int elem_bytes,
+                               const void* gathered_dev, void* frame_dev, void* stream);
 
 /* Tile list helpers (chunk, Glome.hs:371-377): number of tiles and tile i's rect, in the order
  * renderTiles enumerates them (x-major). */

@@ -36,7 +36,7 @@ def _worker(rank, world, port, q):
     ok = True
     for mode in (L.MODE_ONE_RAY, L.MODE_ADAPTIVE_AA):
         w, h = 640, 360
-        rdr = ShardedRenderer(sc, cam, w, h, mode, rec, rank=rank, world=world)
+        rdr = ShardedRenderer(sc, cam, w, h, mode, rec, rank=rank, world=world, want_tcolor=True)
         rdr.render_frame_dev()
         torch.cuda.synchronize()
         full = rdr.tcolor.cpu().numpy()
