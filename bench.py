@@ -256,16 +256,20 @@ def main():
     ms_per_step = total_ms / args.steps
     value = rays_frame / (ms_per_step * 1e-3) / 1e6
 
-    # ---- timed: the dominant kernel alone (roofline), events on the launching stream ----
+    # ---- timed: the dominant kernel alone (roofline): the persistent BIH traversal kernel, closest-hit + any-hit
+    # launches of one frame, bracketed by CUDA events on the launching stream inside glome_render_dev ----
     opts1 = G.render_opts(mode=L.MODE_ONE_RAY, recurs=recurs, tile_first=rank, tile_stride=world)
-    kt = []
+    kt, tt, tl = [], [], 0
     for _ in range(min(args.steps, 10)):
         flush.fill_(1)
         torch.cuda.synchronize()
         s1 = scene.render_ptr(cam, WIDTH, HEIGHT, opts1, rdr.tcolor.data_ptr(), 0, dev=True,
                               stream=torch.cuda.current_stream().cuda_stream)
         kt.append(s1.kernel_ms)
+        tt.append(s1.traverse_ms)
+        tl = s1.traverse_launches
     kern_ms = float(np.mean(kt))
+    trav_ms = float(np.mean(tt))
 
     # ---- timed: end to end through the C-ABI with host buffers (e2e) ----
     e2e_ms = []
@@ -293,12 +297,18 @@ def main():
 
     if rank == 0:
         peaks, which = measured_peaks()
-        # algorithmic bytes of one launch of the dominant kernel on this rank (DESIGN.md "Roofline"):
-        # BIH branch 32 B, sphere record 32 B, BVH branch 128 B, triangle 32 B Tri + 72 B vertices, 40 B TColor out
+        # algorithmic bytes of the traversal launches of one frame on this rank: BIH branch 32 B,
+        # sphere record 32 B, BVH branch 128 B, triangle 32 B Tri + 72 B vertices, 24 B hit record out per ray
         stl = rdr.last_stats
-        npix_rank = stl.rays_primary
-        alg_bytes = (stl.visits_bih * 32 + stl.tests_prim * 32 + stl.visits_bvh * 128 + stl.tests_tri * 104 + npix_rank * 40)
-        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+        rays_rank = stl.rays_primary + stl.rays_shadow
+        alg_bytes = (stl.visits_bih * 32 + stl.tests_prim * 32 + stl.visits_bvh * 128 + stl.tests_tri * 104 + rays_rank * 24)
+        achieved = alg_bytes / (trav_ms * 1e-3) / 1e9
+        traffic = None
+        try:  # DRAM bytes of the same launches from the committed ncu capture (profiles/), N=1 only
+            if world == 1:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["dram_bytes_per_frame_traversal"]
+        except Exception:
+            pass
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -313,8 +323,9 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": which,
-                         "kernel": "k_bih_traverse<closest> + k_surface + k_bih_traverse<any> + k_shade (one wave)", "kernel_ms": kern_ms,
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": which,
+                         "kernel": "k_bih_traverse (persistent BIH traversal): %d launches per frame, closest-hit + any-hit" % tl,
+                         "kernel_ms": trav_ms, "share_of_step": trav_ms / kern_ms, "frame_kernels_ms": kern_ms,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "visits": {"bih_branch": stl.visits_bih, "sphere_tests": stl.tests_prim},
                          "note": "working set (~96 MB) is L2-resident: see profiles/ for L2 and issue-slot figures"},

@@ -427,6 +427,9 @@ struct GlomeScene {
     double* w_surf; unsigned int* w_occl; int2* w_squeue; int* w_squeue_count;
     unsigned int* w_counters;  // one work counter per persistent launch of a frame
     int w_counter_next;
+    std::vector<cudaEvent_t> tev;  // start/stop pairs around the traversal kernels of the last timed frame
+    int tev_used;
+    bool time_traversal;
     int n_scene_lights;
 };
 
@@ -578,6 +581,7 @@ extern "C" int glome_scene_create(const GlomeFlatScene* desc, int device, GlomeS
     s->w_hit_t = nullptr; s->w_hit_seg = s->w_hit_item = s->w_hit_sub = s->w_hit_flags = nullptr;
     s->w_surf = nullptr; s->w_occl = nullptr; s->w_squeue = nullptr; s->w_squeue_count = nullptr; s->w_counters = nullptr;
     s->w_counter_next = 0;
+    s->tev_used = 0; s->time_traversal = false;
     s->n_scene_lights = ls[1];
     if (s->scene_class == GLOME_CLASS_FLAT && !getenv("GLOME_FLAT_MEGAKERNEL") && build_segments(desc, s->segs) &&
         ls[0] + ls[1] <= 32) {
@@ -605,6 +609,7 @@ extern "C" int glome_scene_destroy(GlomeScene* s) {
     cudaFree(s->w_hit_flags); cudaFree(s->w_surf); cudaFree(s->w_occl); cudaFree(s->w_squeue); cudaFree(s->w_squeue_count);
     cudaFree(s->w_counters);
     cudaEventDestroy(s->ev0); cudaEventDestroy(s->ev1);
+    for (cudaEvent_t e : s->tev) cudaEventDestroy(e);
     delete s;
     return GLOME_OK;
 }
@@ -701,6 +706,8 @@ static void read_stats(GlomeScene* s, GlomeRenderStats* out, float ms, int launc
     out->kernel_ms = ms;
     out->launches = launches;
     out->reserved = 0;
+    out->traverse_ms = 0;
+    out->traverse_launches = 0;
     out->visits_bih = (int64_t)h.bih;
     out->tests_prim = (int64_t)h.prim;
     out->visits_bvh = (int64_t)h.bvh;
@@ -818,6 +825,16 @@ static int persistent_grid(GlomeScene* s, K kernel, int threads) {
     return s->sm_count * b;
 }
 
+static void trav_mark(GlomeScene* s, cudaStream_t st) {
+    if (!s->time_traversal) return;
+    if (s->tev_used >= (int)s->tev.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        s->tev.push_back(e);
+    }
+    cudaEventRecord(s->tev[s->tev_used++], st);
+}
+
 // One trace wave over the sample list described by W (mode / queue): K1 per segment, K2a, K1' per segment, K2b.
 static int launch_wave(GlomeScene* s, gwave::WaveParams W, long long max_samples, cudaStream_t st) {
     using namespace gwave;
@@ -841,11 +858,15 @@ static int launch_wave(GlomeScene* s, gwave::WaveParams W, long long max_samples
         if (sg.kind == SEG_BIH) {
             bool linear = (s->segs_linear[i] != 0);
             unsigned int* ctr = s->w_counters + (s->w_counter_next++ & 1023);
+            trav_mark(s, st);
             if (linear) k_bih_traverse<false, true><<<g_bih[1], GW_THREADS, 0, st>>>(s->d, W, (int)i, sg, ctr);
             else k_bih_traverse<false, false><<<g_bih[0], GW_THREADS, 0, st>>>(s->d, W, (int)i, sg, ctr);
+            trav_mark(s, st);
         } else if (sg.kind == SEG_MESH) {
             unsigned int* ctr = s->w_counters + (s->w_counter_next++ & 1023);
+            trav_mark(s, st);
             k_bvh_closest<<<g_bvh, 128, 0, st>>>(s->d, W, (int)i, sg, ctr);
+            trav_mark(s, st);
         } else {
             k_prims_closest<<<sgrid, 128, 0, st>>>(s->d, W, (int)i, sg);
         }
@@ -861,8 +882,10 @@ static int launch_wave(GlomeScene* s, gwave::WaveParams W, long long max_samples
             if (sg.kind == SEG_BIH) {
                 bool linear = (s->segs_linear[i] != 0);
                 unsigned int* ctr = s->w_counters + (s->w_counter_next++ & 1023);
+                trav_mark(s, st);
                 if (linear) k_bih_traverse<true, true><<<g_bih[3], GW_THREADS, 0, st>>>(s->d, W, (int)i, sg, ctr);
                 else k_bih_traverse<true, false><<<g_bih[2], GW_THREADS, 0, st>>>(s->d, W, (int)i, sg, ctr);
+                trav_mark(s, st);
             } else if (sg.kind == SEG_PRIMS) {
                 k_prims_any<<<sgrid, 128, 0, st>>>(s->d, W, sg);
             } else continue;  // a Mesh casts no shadows (Mesh.hs:210)
@@ -888,6 +911,8 @@ extern "C" int glome_render_dev(GlomeScene* s, const GlomeCamera* cam, int width
     if (n_sel < 0) n_sel = 0;
     int launches0 = s->launches;
     size_t npix = (size_t)width * height;
+    s->time_traversal = (stats != nullptr);
+    s->tev_used = 0;
     CK(cudaMemsetAsync(s->stats, 0, sizeof(DevStats), st));
     CK(cudaEventRecord(s->ev0, st));
     TraceParams P;
@@ -982,6 +1007,13 @@ extern "C" int glome_render_dev(GlomeScene* s, const GlomeCamera* cam, int width
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
         read_stats(s, stats, ms, s->launches - launches0);
+        double tms = 0;
+        for (int k = 0; k + 1 < s->tev_used; k += 2) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, s->tev[k], s->tev[k + 1]) == cudaSuccess) tms += t;
+        }
+        stats->traverse_ms = tms;
+        stats->traverse_launches = s->tev_used / 2;
     }
     return GLOME_OK;
 }

@@ -237,6 +237,8 @@ typedef struct GlomeRenderStats {
     int64_t tests_prim;     /* primitive records tested (sphere 32 B, ...)            */
     int64_t visits_bvh;     /* Mesh BVH branch nodes loaded (128 B each)              */
     int64_t tests_tri;      /* mesh triangles tested (32 B Tri + 72 B vertices)       */
+    double traverse_ms;     /* device time of the traversal kernels alone (K1 + K1'), CUDA events   */
+    int64_t traverse_launches;
 } GlomeRenderStats;
 
 typedef struct GlomeScene GlomeScene; /* opaque device-resident scene */
