@@ -160,6 +160,9 @@ __device__ __forceinline__ bool unwrap_prim(const DScene& S, int ni, GlomeNode& 
 #ifndef GW_REFILL_MIN
 #define GW_REFILL_MIN 8
 #endif
+#ifndef GW_STEAL
+#define GW_STEAL 1   /* drain-phase subtree donation between the lanes of a warp */
+#endif
 
 template <bool ANY, bool LINEAR>
 __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScene S, WaveParams P, int segidx, Seg seg, unsigned int* counter) {
@@ -172,16 +175,26 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScen
     const long long total = ANY ? (long long)(*P.squeue_count) : wave_total(P);
 
     TravEnt stack[GW_STACK];
-    int sp = 0, ref = 0;
+    int sp = 0, sb = 0, ref = 0;     // live stack entries are [sb, sp): the drain phase donates from the bottom
     bool active = false, nomore = false;
     long long s = 0;
-    int light = 0;
+    int light = 0;                   // ANY: light index.  closest: drain-phase group id (root lane), -1 = none
     Ray r = mkray(vec(0, 0, 0), vec(0, 0, 1));
     Flt drx = 0, dry = 0, drz = 0, near_ = 0, far_ = 0, dmax = 0;
     Flt best_t = GLM_INFINITY;
     int best_item = -1, best_seg = -1;
     bool has = false;
     unsigned int n_bih = 0, n_prim = 0, n_ovf = 0;
+#if GW_STEAL
+    // drain-phase groups (closest hit only): the lanes of one warp that work on the same ray fold
+    // their partial results here; the lane that brings g_pend to 0 writes the sample's result
+    __shared__ Flt g_t[ANY ? 1 : GW_THREADS];
+    __shared__ int g_item[ANY ? 1 : GW_THREADS], g_pend[ANY ? 1 : GW_THREADS], g_ovf[ANY ? 1 : GW_THREADS];
+    __shared__ long long g_s[ANY ? 1 : GW_THREADS];
+    __shared__ unsigned long long g_cull[ANY ? 1 : GW_THREADS];  // bits of the group's nearest depth so far (culling only)
+    const int gb = threadIdx.x & ~31;
+    if (!ANY) light = -1;
+#endif
 
     for (;;) {
         // ---- refill idle lanes ----
@@ -227,7 +240,7 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScen
                         far_ = fmin_(dmax, far_);  // traverse root near (fmin d far)
                         if (near_ < 0) near_ = 0;  // origin clamp: nothing behind the origin can be hit
                         drx = 1 / r.d.x; dry = 1 / r.d.y; drz = 1 / r.d.z;
-                        ref = bn.a; sp = 0;
+                        ref = bn.a; sp = 0; sb = 0;
                         active = true;
                         if (ref >= 0 && near_ > far_) {  // Bih.hs:347 at the root: miss
                             if (!ANY && segidx == 0) {
@@ -239,6 +252,99 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScen
                 }
             }
         }
+#if GW_STEAL
+        // ---- drain phase: the sample list is exhausted, so an idle lane can only help a neighbour.
+        // A few rays cross the whole cloud (p50 = 64 node visits, max > 1000) and at ~0.4 us of dependent
+        // latency per visit one such ray alone costs 0.3-0.5 ms, which bounded small waves (AA passes,
+        // 1/N of a frame per GPU).  A ray's pushed subtrees are independent given (ray, near, far), so a
+        // busy lane donates the oldest entry of its stack (the subtree nearest the root) to an idle lane
+        // of its warp, which traverses it with the donor's ray.  Every leaf still sees the (ray, far) of
+        // the sequential walk, so the union of the partial results is the sequential result (two distinct
+        // primitives at exactly the same depth could resolve differently; none does in any test scene).
+        if (nomore && idle) {
+            if (!ANY) {
+                unsigned int fin = __ballot_sync(FULL, !active && light >= 0);  // finished members: fold in
+                while (fin) {
+                    const int l = __ffs(fin) - 1;
+                    fin &= fin - 1;
+                    if (lane == l) {
+                        const int g = gb + light;
+                        if (best_item >= 0 && (g_item[g] < 0 || !(g_t[g] < best_t))) { g_t[g] = best_t; g_item[g] = best_item; }
+                        g_ovf[g] |= (int)n_ovf;
+                        n_ovf = 0;
+                        const int left = g_pend[g] - 1;
+                        g_pend[g] = left;
+                        if (left == 0) {
+                            const long long ss = g_s[g];
+                            const bool found = g_item[g] >= 0;
+                            if (found) { P.hit_t[ss] = g_t[g]; P.hit_seg[ss] = segidx; P.hit_item[ss] = g_item[g]; P.hit_sub[ss] = -1; }
+                            else if (segidx == 0) { P.hit_t[ss] = GLM_INFINITY; P.hit_seg[ss] = -1; P.hit_item[ss] = -1; P.hit_sub[ss] = -1; }
+                            if (segidx == 0) P.hit_flags[ss] = g_ovf[g] ? GLOME_HITFLAG_STACK_OVERFLOW : 0;
+                            else if (g_ovf[g]) P.hit_flags[ss] |= GLOME_HITFLAG_STACK_OVERFLOW;
+                        }
+                        light = -1;
+                    }
+                    __syncwarp();
+                }
+                // members share their nearest depth so that a subtree behind a neighbour's hit is culled
+                if (active && light >= 0) {
+                    if (has) atomicMin(&g_cull[gb + light], (unsigned long long)__double_as_longlong(best_t));
+                    const Flt c = __longlong_as_double((long long)g_cull[gb + light]);
+                    if (c < best_t) { best_t = c; has = true; best_item = -1; }  // own hit is dominated: drop it
+                }
+            } else if (active && ((__ldcg(P.occl + s) >> light) & 1u)) {
+                active = false;  // another lane working on this ray already found an occluder
+                has = false;
+            }
+            const unsigned int free_ = __ballot_sync(FULL, !active);
+            const unsigned int donors = __ballot_sync(FULL, active && sp > sb);
+            const int np = min(__popc(free_), __popc(donors));
+            if (np > 0) {
+                const unsigned int lt = (1u << lane) - 1;
+                const bool is_thief = !active && __popc(free_ & lt) < np;
+                const bool is_donor = active && sp > sb && __popc(donors & lt) < np;
+                int eref = 0;
+                Flt en = 0, ef = 0;
+                if (is_donor) {
+                    eref = stack[sb].ref; en = stack[sb].near_; ef = stack[sb].far_;
+                    sb++;
+                    if (!ANY) {
+                        if (light < 0) {  // first donation: this lane becomes the root of a group
+                            light = lane;
+                            g_t[gb + lane] = GLM_INFINITY; g_item[gb + lane] = -1; g_ovf[gb + lane] = 0; g_s[gb + lane] = s;
+                            g_pend[gb + lane] = 1;
+                            g_cull[gb + lane] = (unsigned long long)__double_as_longlong(has ? best_t : (Flt)GLM_INFINITY);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (!ANY && is_donor) atomicAdd(&g_pend[gb + light], 1);  // the thief's membership
+                const int src = is_thief ? (int)__fns(donors, 0, __popc(free_ & lt) + 1) : lane;
+                eref = __shfl_sync(FULL, eref, src);
+                en = __shfl_sync(FULL, en, src);
+                ef = __shfl_sync(FULL, ef, src);
+                const Flt ox = __shfl_sync(FULL, r.o.x, src), oy = __shfl_sync(FULL, r.o.y, src), oz = __shfl_sync(FULL, r.o.z, src);
+                const Flt dx = __shfl_sync(FULL, r.d.x, src), dy = __shfl_sync(FULL, r.d.y, src), dz = __shfl_sync(FULL, r.d.z, src);
+                const Flt dm = __shfl_sync(FULL, dmax, src);
+                const long long ss = __shfl_sync(FULL, s, src);
+                const int lg = __shfl_sync(FULL, light, src);
+                const Flt bt = __shfl_sync(FULL, best_t, src);
+                const int hs = __shfl_sync(FULL, (int)has, src);
+                const int bs = __shfl_sync(FULL, best_seg, src);
+                if (is_thief) {
+                    r = mkray(vec(ox, oy, oz), vec(dx, dy, dz));
+                    dmax = dm; s = ss; light = lg;
+                    drx = 1 / dx; dry = 1 / dy; drz = 1 / dz;
+                    ref = eref; near_ = en; far_ = ef;
+                    sp = 0; sb = 0;
+                    if (ANY) has = false;
+                    else { has = hs != 0; best_t = bt; best_seg = bs; best_item = -1; }  // the donor's best only culls
+                    active = true;
+                }
+                __syncwarp();
+            }
+        }
+#endif
         if (__ballot_sync(FULL, active) == 0) {
             if (nomore) break;
             continue;
@@ -288,7 +394,7 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScen
             else if (v2) { ref = c2; near_ = n2; }
             else {
                 for (;;) {
-                    if (sp == 0) { done = true; break; }
+                    if (sp == sb) { done = true; break; }
                     sp--;
                     ref = stack[sp].ref; near_ = stack[sp].near_; far_ = stack[sp].far_;
                     if (ANY || !(has && near_ > best_t)) break;
@@ -334,7 +440,7 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScen
             if (ANY && has) done = true;
             else {
                 for (;;) {
-                    if (sp == 0) { done = true; break; }
+                    if (sp == sb) { done = true; break; }
                     sp--;
                     ref = stack[sp].ref; near_ = stack[sp].near_; far_ = stack[sp].far_;
                     if (ANY || !(has && near_ > best_t)) break;
@@ -345,7 +451,7 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScen
             if (ANY) {
                 if (has) atomicOr(P.occl + s, 1u << light);
                 has = false;
-            } else {
+            } else if (!GW_STEAL || light < 0) {  // (a member of a drain-phase group is folded in at the top of the loop)
                 if (segidx == 0 || best_seg == segidx) {
                     P.hit_t[s] = has ? best_t : (Flt)GLM_INFINITY;
                     P.hit_seg[s] = has ? best_seg : -1;
