@@ -160,6 +160,18 @@ __device__ __forceinline__ bool unwrap_prim(const DScene& S, int ni, GlomeNode& 
 #ifndef GW_REFILL_MIN
 #define GW_REFILL_MIN 8
 #endif
+#ifndef GW_GUIDED
+#define GW_GUIDED 1  /* guided self-scheduling of the sample list */
+#endif
+#ifndef GW_GUIDED_MIN
+#define GW_GUIDED_MIN 4
+#endif
+#ifndef GW_MAXBATCH
+#define GW_MAXBATCH 32
+#endif
+#ifndef GW_STEAL_AFTER
+#define GW_STEAL_AFTER 0
+#endif
 #ifndef GW_STEAL
 #define GW_STEAL 1   /* drain-phase subtree donation between the lanes of a warp */
 #endif
@@ -185,6 +197,11 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScen
     int best_item = -1, best_seg = -1;
     bool has = false;
     unsigned int n_bih = 0, n_prim = 0, n_ovf = 0;
+    unsigned int n_start = 0;        // n_bih when the lane's current ray started
+#if GW_GUIDED
+    unsigned int next_base = 0;
+    const long long nwarps = (long long)gridDim.x * (GW_THREADS / 32);
+#endif
 #if GW_STEAL
     // drain-phase groups (closest hit only): the lanes of one warp that work on the same ray fold
     // their partial results here; the lane that brings g_pend to 0 writes the sample's result
@@ -204,12 +221,22 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScen
         if (__popc(idle) >= GW_REFILL_MIN && !nomore) {
             unsigned int base = 0;
             int cnt = __popc(idle);
+#if GW_GUIDED
+            // guided self-scheduling: batches shrink as the list drains (and are small from the start when the
+            // wave has fewer samples than lanes), so the expensive pixels of one screen tile end up on many
+            // warps, each with idle lanes to share them, instead of 32 on one
+            cnt = min(cnt, (int)min((long long)GW_MAXBATCH, max((long long)GW_GUIDED_MIN, (total - (long long)next_base) / (2LL * nwarps) + 1)));
+#endif
             int leader = __ffs(idle) - 1;
             if (lane == leader) base = atomicAdd(counter, (unsigned int)cnt);
             base = __shfl_sync(FULL, base, leader);
             if ((long long)base + cnt >= total) nomore = true;
-            if (!active) {
-                long long w = (long long)base + __popc(idle & ((1u << lane) - 1));
+#if GW_GUIDED
+            next_base = base + (unsigned int)cnt;
+#endif
+            const int rank = __popc(idle & ((1u << lane) - 1));
+            if (!active && rank < cnt) {
+                long long w = (long long)base + rank;
                 if (w < total) {
                     bool ok;
                     if (ANY) {
@@ -241,6 +268,7 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScen
                         if (near_ < 0) near_ = 0;  // origin clamp: nothing behind the origin can be hit
                         drx = 1 / r.d.x; dry = 1 / r.d.y; drz = 1 / r.d.z;
                         ref = bn.a; sp = 0; sb = 0;
+                        n_start = n_bih;
                         active = true;
                         if (ref >= 0 && near_ > far_) {  // Bih.hs:347 at the root: miss
                             if (!ANY && segidx == 0) {
@@ -261,6 +289,12 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScen
         // of its warp, which traverses it with the donor's ray.  Every leaf still sees the (ray, far) of
         // the sequential walk, so the union of the partial results is the sequential result (two distinct
         // primitives at exactly the same depth could resolve differently; none does in any test scene).
+        // members of a group share their nearest depth every round, so that a subtree behind a neighbour's hit is culled
+        if (!ANY && nomore && active && light >= 0) {
+            if (has) atomicMin(&g_cull[gb + light], (unsigned long long)__double_as_longlong(best_t));
+            const Flt c = __longlong_as_double((long long)g_cull[gb + light]);
+            if (c < best_t) { best_t = c; has = true; best_item = -1; }  // own hit is dominated: drop it
+        }
         if (nomore && idle) {
             if (!ANY) {
                 unsigned int fin = __ballot_sync(FULL, !active && light >= 0);  // finished members: fold in
@@ -286,23 +320,22 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScen
                     }
                     __syncwarp();
                 }
-                // members share their nearest depth so that a subtree behind a neighbour's hit is culled
-                if (active && light >= 0) {
-                    if (has) atomicMin(&g_cull[gb + light], (unsigned long long)__double_as_longlong(best_t));
-                    const Flt c = __longlong_as_double((long long)g_cull[gb + light]);
-                    if (c < best_t) { best_t = c; has = true; best_item = -1; }  // own hit is dominated: drop it
-                }
             } else if (active && ((__ldcg(P.occl + s) >> light) & 1u)) {
                 active = false;  // another lane working on this ray already found an occluder
                 has = false;
             }
             const unsigned int free_ = __ballot_sync(FULL, !active);
-            const unsigned int donors = __ballot_sync(FULL, active && sp > sb);
+            // GW_STEAL_AFTER > 0 lets only rays that already walked that many nodes donate (a typical ray ends at a near
+            // hit that culls its pending subtrees, so walking those in parallel is wasted work).  Measured on B200: the
+            // greedy setting (0) does up to 2x the node visits on small waves and is still the fastest (720x480 AA:
+            // 4.26 ms vs 4.70 ms at 128 and 5.26 ms at 256), because those waves are latency-bound, not issue-bound.
+            const bool can_give = active && sp > sb && (GW_STEAL_AFTER == 0 || (n_bih - n_start) >= GW_STEAL_AFTER);
+            const unsigned int donors = __ballot_sync(FULL, can_give);
             const int np = min(__popc(free_), __popc(donors));
             if (np > 0) {
                 const unsigned int lt = (1u << lane) - 1;
                 const bool is_thief = !active && __popc(free_ & lt) < np;
-                const bool is_donor = active && sp > sb && __popc(donors & lt) < np;
+                const bool is_donor = can_give && __popc(donors & lt) < np;
                 int eref = 0;
                 Flt en = 0, ef = 0;
                 if (is_donor) {
@@ -337,6 +370,7 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScen
                     drx = 1 / dx; dry = 1 / dy; drz = 1 / dz;
                     ref = eref; near_ = en; far_ = ef;
                     sp = 0; sb = 0;
+                    n_start = n_bih - GW_STEAL_AFTER;  // a piece of a long ray may be split further at once
                     if (ANY) has = false;
                     else { has = hs != 0; best_t = bt; best_seg = bs; best_item = -1; }  // the donor's best only culls
                     active = true;
@@ -495,18 +529,29 @@ __global__ void __launch_bounds__(128, 3) k_bvh_closest(DScene S, WaveParams P, 
     int best_sub = -1, best_seg = -1;
     bool has = false;
     unsigned int n_bvh = 0, n_tri = 0, n_ovf = 0;
+#if GW_GUIDED
+    unsigned int next_base = 0;
+    const long long nwarps = (long long)gridDim.x * 4;
+#endif
 
     for (;;) {
         unsigned int idle = __ballot_sync(FULL, !active);
         if (idle && !nomore) {
             unsigned int base = 0;
             int cnt = __popc(idle);
+#if GW_GUIDED
+            cnt = min(cnt, (int)min((long long)GW_MAXBATCH, max((long long)GW_GUIDED_MIN, (total - (long long)next_base) / (2LL * nwarps) + 1)));
+#endif
             int leader = __ffs(idle) - 1;
             if (lane == leader) base = atomicAdd(counter, (unsigned int)cnt);
             base = __shfl_sync(FULL, base, leader);
             if ((long long)base + cnt >= total) nomore = true;
-            if (!active) {
-                long long w = (long long)base + __popc(idle & ((1u << lane) - 1));
+#if GW_GUIDED
+            next_base = base + (unsigned int)cnt;
+#endif
+            const int rank = __popc(idle & ((1u << lane) - 1));
+            if (!active && rank < cnt) {
+                long long w = (long long)base + rank;
                 if (w < total) {
                     s = w;
                     int x, y;
