@@ -120,6 +120,8 @@ SIGNATURES = {
     "glome_tile_rect": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _ip]),
     "glome_builder_create": (C.c_int, [_P(_vp)]),
     "glome_builder_destroy": (C.c_int, [_vp]),
+    "glome_builder_set_build_device": (C.c_int, [_vp, C.c_int]),
+    "glome_builder_last_build_ms": (C.c_int, [_vp, _dp]),
     "glome_sb_void": (C.c_int, [_vp]),
     "glome_sb_sphere": (C.c_int, [_vp, _dp, C.c_double]),
     "glome_sb_spheres": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp]),
@@ -167,6 +169,7 @@ SIGNATURES = {
     "glome_sb_flatten": (C.c_int, [_vp, C.c_int, _P(GlomeFlatScene)]),
     "glome_sb_config_scene": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_uint64, _P(GlomeCamera), _ip]),
     "glome_bih_build": (C.c_int, [C.c_int64, _vp, _P(_P(GlomeBihNode)), _ip, _P(_ip), _ip, _P(_ip), _ip, _dp]),
+    "glome_bih_build_gpu": (C.c_int, [C.c_int64, _vp, C.c_int, _P(_P(GlomeBihNode)), _ip, _P(_ip), _ip, _P(_ip), _ip, _dp, _dp]),
     "glome_mesh_build": (C.c_int, [C.c_int64, _vp, C.c_int64, _vp, _P(_P(GlomeBvhNode)), _ip, _P(_ip), _ip,
                                    _P(_ip), _ip, _ip, _dp]),
     "glome_free": (None, [_vp]),

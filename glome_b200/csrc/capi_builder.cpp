@@ -5,6 +5,7 @@
 #include <string>
 
 #include "host_builder.h"
+#include "glome_build.h"
 
 using namespace glome_host;
 using glm::Vec;
@@ -31,6 +32,16 @@ int glome_builder_create(GlomeBuilder** out) {
     return GLOME_OK;
 }
 int glome_builder_destroy(GlomeBuilder* b) { delete b; return GLOME_OK; }
+int glome_builder_set_build_device(GlomeBuilder* b, int device) {
+    if (!b) return GLOME_EINVAL;
+    b->b.build_device = device;
+    return GLOME_OK;
+}
+int glome_builder_last_build_ms(GlomeBuilder* b, double out[4]) {
+    if (!b || !out) return GLOME_EINVAL;
+    memcpy(out, b->b.build_ms, sizeof(double) * 4);
+    return GLOME_OK;
+}
 
 int glome_sb_void(GlomeBuilder* b) { GUARD(b->b.void_()); }
 int glome_sb_sphere(GlomeBuilder* b, const double c[3], double r) { GUARD(b->b.sphere(V(c), r)); }
@@ -151,11 +162,26 @@ int glome_sb_config_scene(GlomeBuilder* b, int config, int64_t n, uint64_t seed,
     GUARD(config_scene(b->b, config, n, seed, cam, recurs_out));
 }
 
+static int bih_build_any(int64_t n, const double* bboxes, int device, double* timings_ms, GlomeBihNode** nodes_out,
+                         int32_t* n_nodes_out, int32_t** leaves_out, int32_t* n_leaves_out, int32_t** item_order_out,
+                         int32_t* root_ref_out, double bb_out[6]);
 int glome_bih_build(int64_t n, const double* bboxes, GlomeBihNode** nodes_out, int32_t* n_nodes_out, int32_t** leaves_out,
                     int32_t* n_leaves_out, int32_t** item_order_out, int32_t* root_ref_out, double bb_out[6]) {
+    return bih_build_any(n, bboxes, -1, nullptr, nodes_out, n_nodes_out, leaves_out, n_leaves_out, item_order_out, root_ref_out, bb_out);
+}
+int glome_bih_build_gpu(int64_t n, const double* bboxes, int device, GlomeBihNode** nodes_out, int32_t* n_nodes_out,
+                        int32_t** leaves_out, int32_t* n_leaves_out, int32_t** item_order_out, int32_t* root_ref_out,
+                        double bb_out[6], double timings_ms[3]) {
+    if (device < 0) { glome_set_error("glome_bih_build_gpu needs a device index"); return GLOME_ENODEV; }
+    return bih_build_any(n, bboxes, device, timings_ms, nodes_out, n_nodes_out, leaves_out, n_leaves_out, item_order_out, root_ref_out, bb_out);
+}
+static int bih_build_any(int64_t n, const double* bboxes, int device, double* timings_ms, GlomeBihNode** nodes_out,
+                         int32_t* n_nodes_out, int32_t** leaves_out, int32_t* n_leaves_out, int32_t** item_order_out,
+                         int32_t* root_ref_out, double bb_out[6]) {
     try {
         BihTree t;
-        bih_build(n, bboxes, t);
+        if (device >= 0) bih_build_gpu(n, bboxes, device, t, timings_ms);
+        else bih_build(n, bboxes, t);
         *n_nodes_out = (int32_t)t.nodes.size();
         *n_leaves_out = (int32_t)(t.leaves.size() / 2);
         *nodes_out = (GlomeBihNode*)malloc(sizeof(GlomeBihNode) * (t.nodes.size() + 1));

@@ -1,0 +1,526 @@
+// glome_build.cu -- the reference's BIH builder (`bih` / `build_rec`, Bih.hs:211-324) on the GPU.
+//
+// The reference builds the tree by recursive list partition; host_builder.cpp does the same with index
+// ranges.  Here the recursion is turned into a level-synchronous sweep over the item array:
+//
+//   per level   k_accum    every item of a pending node evaluates the four candidate partitions (x, y, z mid
+//                          split, big/small, Bih.hs:218-232) and folds count / lmax / rmin into its node's
+//                          accumulators (warp- and block-aggregated while a block sits inside one node)
+//               k_decide   one thread per node: costs, leaf rule and the (sic) selection chain (Bih.hs:252-285),
+//                          child boxes; allocates the two children
+//               k_scan_*   exclusive scan of the "goes left" flag over the whole array
+//               k_scatter  stable partition of every splitting node at once: left rank = S[p] - S[lo]
+//   afterwards  k_sizes / k_number / k_emit: subtree sizes bottom-up, pre-order numbers top-down, and the
+//               node / leaf arrays in exactly the layout bih_build() produces.
+//
+// Arithmetic is glome_math.h compiled with -fmad=false, and the min / max folds are order-independent for the
+// finite values involved, so the tree is the host builder's tree bit for bit (tests/test_gpu_build.py).
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "glome_build.h"
+
+namespace glome_host {
+namespace {
+
+using namespace glm;
+
+#define BK(x)                                                                                              \
+    do {                                                                                                   \
+        cudaError_t e_ = (x);                                                                              \
+        if (e_ != cudaSuccess) throw BuildError(std::string("bih_build_gpu: ") + #x + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+enum { ST_PENDING = 0, ST_BRANCH = 1, ST_LEAF = 2 };
+enum { ERR_DEPTH = 1, ERR_NODES = 2 };
+#define BUILD_MAX_DEPTH 512 /* host_builder.cpp's guard */
+
+struct BNode {
+    int lo, hi;         // item positions [lo, hi)
+    int state, k;       // k: winning partition 0..2 = x,y,z, 3 = big/small
+    int left, right;    // children (node ids)
+    int split, depth;   // first position of the right child
+    double bb[6];
+    double mid[3];
+    double thresh;      // 0.4 * bbsa'(bb)   (Bih.hs:223)
+    double lmax, rmin;  // of the winning partition
+};
+
+struct LevelAcc {       // accumulators of one node of the current level
+    int lc[4];
+    unsigned long long lmax[4], rmin[4];  // order-preserving keys
+};
+
+struct Counters { int n_nodes, n_pending, err, pad; };
+
+// order-preserving map double -> uint64 (for atomicMax / atomicMin)
+__device__ __forceinline__ unsigned long long f2key(double x) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key2f(unsigned long long k) {
+    unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+__device__ __forceinline__ Flt bbsa_p(const Bbox& b) { return hmax(0, bbsa(b)); }  // Bih.hs:208
+__device__ __forceinline__ Bbox ldbb6(const double* b) { return mkbb(vec(b[0], b[1], b[2]), vec(b[3], b[4], b[5])); }
+
+__device__ __forceinline__ unsigned long long warp_max(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
+    return v;
+}
+__device__ __forceinline__ unsigned long long warp_min(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o); v = w < v ? w : v; }
+    return v;
+}
+
+// per item: bbmid and bbsa' of its box; the BIH's box = foldl' bbjoin empty_bbox (Bih.hs:315)
+__global__ void k_prep(int n, const double* __restrict__ bb, double* __restrict__ mid, double* __restrict__ sa,
+                       int* __restrict__ idx, int* __restrict__ node_of, unsigned long long* bbkeys) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long lo[3], hi[3];
+    const unsigned long long KMAX = f2key(GLM_INFINITY), KMIN = f2key(-GLM_INFINITY);
+    for (int a = 0; a < 3; a++) { lo[a] = KMAX; hi[a] = KMIN; }
+    if (i < n) {
+        Bbox ob = ldbb6(bb + 6 * (size_t)i);
+        Vec m = bbmid(ob);
+        mid[3 * (size_t)i] = m.x; mid[3 * (size_t)i + 1] = m.y; mid[3 * (size_t)i + 2] = m.z;
+        sa[i] = bbsa_p(ob);
+        idx[i] = i;
+        node_of[i] = 0;
+        lo[0] = f2key(ob.p1.x); lo[1] = f2key(ob.p1.y); lo[2] = f2key(ob.p1.z);
+        hi[0] = f2key(ob.p2.x); hi[1] = f2key(ob.p2.y); hi[2] = f2key(ob.p2.z);
+    }
+    for (int a = 0; a < 3; a++) { lo[a] = warp_min(lo[a]); hi[a] = warp_max(hi[a]); }
+    if ((threadIdx.x & 31) == 0)
+        for (int a = 0; a < 3; a++) { atomicMin(bbkeys + a, lo[a]); atomicMax(bbkeys + 3 + a, hi[a]); }
+}
+
+__device__ __forceinline__ void node_set_box(BNode& nd, const Bbox& b) {
+    nd.bb[0] = b.p1.x; nd.bb[1] = b.p1.y; nd.bb[2] = b.p1.z; nd.bb[3] = b.p2.x; nd.bb[4] = b.p2.y; nd.bb[5] = b.p2.z;
+    Vec m = bbmid(b);  // build_rec ... (bbmid childbb)  (Bih.hs:260-274)
+    nd.mid[0] = m.x; nd.mid[1] = m.y; nd.mid[2] = m.z;
+    nd.thresh = bbsa_p(b) * 0.4;
+}
+
+__global__ void k_init_root(int n, const unsigned long long* bbkeys, BNode* nodes, Counters* ctr, double* bb_out) {
+    Bbox b = mkbb(vec(key2f(bbkeys[0]), key2f(bbkeys[1]), key2f(bbkeys[2])), vec(key2f(bbkeys[3]), key2f(bbkeys[4]), key2f(bbkeys[5])));
+    BNode nd;
+    memset(&nd, 0, sizeof(nd));
+    nd.lo = 0; nd.hi = n; nd.depth = 0;
+    nd.state = (n <= 3) ? ST_LEAF : ST_PENDING;  // Bih.hs:214
+    nd.left = nd.right = -1;
+    node_set_box(nd, b);
+    nodes[0] = nd;
+    ctr->n_nodes = 1; ctr->n_pending = (n <= 3) ? 0 : 1; ctr->err = 0;
+    bb_out[0] = b.p1.x; bb_out[1] = b.p1.y; bb_out[2] = b.p1.z; bb_out[3] = b.p2.x; bb_out[4] = b.p2.y; bb_out[5] = b.p2.z;
+}
+
+__global__ void k_acc_reset(int count, LevelAcc* acc) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= count) return;
+    const unsigned long long KMAX = f2key(GLM_INFINITY), KMIN = f2key(-GLM_INFINITY);
+    for (int k = 0; k < 4; k++) { acc[a].lc[k] = 0; acc[a].lmax[k] = KMIN; acc[a].rmin[k] = KMAX; }  // seeds: Bih.hs:225-232
+}
+
+// the four candidate partitions of Bih.hs:218-232, evaluated per item
+__global__ void __launch_bounds__(256) k_accum(int n, int lvl_start, const BNode* __restrict__ nodes, const int* __restrict__ idx,
+                                               const int* __restrict__ node_of, const double* __restrict__ bb,
+                                               const double* __restrict__ mid, const double* __restrict__ sa, LevelAcc* acc) {
+    __shared__ int s_lc[4];
+    __shared__ unsigned long long s_lmax[4], s_rmin[4];
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long KMAX = f2key(GLM_INFINITY), KMIN = f2key(-GLM_INFINITY);
+    int v = -1;
+    bool left[4] = {false, false, false, false};
+    unsigned long long kmaxv[4] = {KMIN, KMIN, KMIN, KMIN}, kminv[4] = {KMAX, KMAX, KMAX, KMAX};
+    if (p < n) {
+        int vv = node_of[p];
+        if (vv >= lvl_start && nodes[vv].state == ST_PENDING) {
+            v = vv;
+            const int i = idx[p];
+            const double* b = bb + 6 * (size_t)i;
+            const double mx = mid[3 * (size_t)i], my = mid[3 * (size_t)i + 1], mz = mid[3 * (size_t)i + 2];
+            const BNode& nd = nodes[v];
+            left[0] = mx < nd.mid[0]; left[1] = my < nd.mid[1]; left[2] = mz < nd.mid[2];
+            left[3] = sa[i] > nd.thresh;
+            // lmax = max p2.k over the left, rmin = min p1.k over the right; big/small uses the x planes (Bih.hs:231-232)
+            if (left[0]) kmaxv[0] = f2key(b[3]); else kminv[0] = f2key(b[0]);
+            if (left[1]) kmaxv[1] = f2key(b[4]); else kminv[1] = f2key(b[1]);
+            if (left[2]) kmaxv[2] = f2key(b[5]); else kminv[2] = f2key(b[2]);
+            if (left[3]) kmaxv[3] = f2key(b[3]); else kminv[3] = f2key(b[0]);
+        }
+    }
+    const unsigned int FULL = 0xffffffffu;
+    const int v0 = __shfl_sync(FULL, v, 0);
+    const bool warp_uniform = __all_sync(FULL, v == v0);
+    // block-uniform: every thread of the block is in the same pending node
+    if (threadIdx.x < 4) { s_lc[threadIdx.x] = 0; s_lmax[threadIdx.x] = KMIN; s_rmin[threadIdx.x] = KMAX; }
+    __shared__ int s_v0;
+    if (threadIdx.x == 0) s_v0 = v;
+    __syncthreads();
+    const bool block_uniform = __syncthreads_and(v == s_v0 && v >= 0) != 0;
+    if (warp_uniform) {
+        if (v0 < 0) return;  // (block_uniform is false then, no barrier follows)
+        int cnt[4];
+        unsigned long long mxk[4], mnk[4];
+        for (int k = 0; k < 4; k++) {
+            cnt[k] = __popc(__ballot_sync(FULL, left[k]));
+            mxk[k] = warp_max(kmaxv[k]);
+            mnk[k] = warp_min(kminv[k]);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (block_uniform) {
+                for (int k = 0; k < 4; k++) { atomicAdd(&s_lc[k], cnt[k]); atomicMax(&s_lmax[k], mxk[k]); atomicMin(&s_rmin[k], mnk[k]); }
+            } else {
+                LevelAcc* A = acc + (v0 - lvl_start);
+                for (int k = 0; k < 4; k++) {
+                    if (cnt[k]) atomicAdd(&A->lc[k], cnt[k]);
+                    if (mxk[k] != KMIN) atomicMax(&A->lmax[k], mxk[k]);
+                    if (mnk[k] != KMAX) atomicMin(&A->rmin[k], mnk[k]);
+                }
+            }
+        }
+    } else if (v >= 0) {
+        LevelAcc* A = acc + (v - lvl_start);
+        for (int k = 0; k < 4; k++) {
+            if (left[k]) { atomicAdd(&A->lc[k], 1); atomicMax(&A->lmax[k], kmaxv[k]); }
+            else atomicMin(&A->rmin[k], kminv[k]);
+        }
+    }
+    if (block_uniform) {
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            LevelAcc* A = acc + (s_v0 - lvl_start);
+            const int k = threadIdx.x;
+            if (s_lc[k]) atomicAdd(&A->lc[k], s_lc[k]);
+            if (s_lmax[k] != KMIN) atomicMax(&A->lmax[k], s_lmax[k]);
+            if (s_rmin[k] != KMAX) atomicMin(&A->rmin[k], s_rmin[k]);
+        }
+    }
+}
+
+__device__ __forceinline__ Bbox set_p2(Bbox b, int ax, Flt f) { if (ax == 0) b.p2.x = f; else if (ax == 1) b.p2.y = f; else b.p2.z = f; return b; }
+__device__ __forceinline__ Bbox set_p1(Bbox b, int ax, Flt f) { if (ax == 0) b.p1.x = f; else if (ax == 1) b.p1.y = f; else b.p1.z = f; return b; }
+
+// build_rec's decision for every pending node of the level (Bih.hs:243-285)
+__global__ void k_decide(int lvl_start, int lvl_end, BNode* nodes, const LevelAcc* __restrict__ acc, Counters* ctr, int max_nodes) {
+    int v = lvl_start + blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= lvl_end) return;
+    BNode nd = nodes[v];
+    if (nd.state != ST_PENDING) return;
+    if (nd.depth > BUILD_MAX_DEPTH) { atomicOr(&ctr->err, ERR_DEPTH); nodes[v].state = ST_LEAF; return; }
+    const LevelAcc A = acc[v - lvl_start];
+    const int n = nd.hi - nd.lo;
+    const Bbox bb = ldbb6(nd.bb);
+    const Flt sa = bbsa_p(bb);
+    Flt lmax[4], rmin[4], cost[4];
+    Bbox lbb[4], rbb[4];
+    for (int k = 0; k < 4; k++) {
+        lmax[k] = key2f(A.lmax[k]); rmin[k] = key2f(A.rmin[k]);
+        const int ax = (k == 3) ? 0 : k;
+        lbb[k] = set_p2(bb, ax, lmax[k]);
+        rbb[k] = set_p1(bb, ax, rmin[k]);
+        const Flt fac = (k == 3) ? 1.2 : 1.1;  // Bih.hs:252-255
+        cost[k] = ((bbsa_p(lbb[k]) * (Flt)A.lc[k]) + (bbsa_p(rbb[k]) * (Flt)(n - A.lc[k]))) * fac;
+    }
+    const Flt costorig = sa * (Flt)n;
+    if (costorig < cost[0] && costorig < cost[1] && costorig < cost[2] && costorig < cost[3]) {  // Bih.hs:276
+        nodes[v].state = ST_LEAF;
+        return;
+    }
+    int k;
+    if (cost[0] < cost[1] && cost[0] < cost[2] && cost[0] < cost[3]) k = 0;
+    else if (cost[1] < cost[2] && cost[1] < cost[3]) k = 1;
+    else if (cost[1] < cost[3]) k = 2;  // sic (Bih.hs:283 tests costy)
+    else k = 3;
+    const int base = atomicAdd(&ctr->n_nodes, 2);
+    if (base + 2 > max_nodes) { atomicOr(&ctr->err, ERR_NODES); nodes[v].state = ST_LEAF; return; }
+    const int split = nd.lo + A.lc[k];
+    BNode l, r;
+    memset(&l, 0, sizeof(l)); memset(&r, 0, sizeof(r));
+    l.lo = nd.lo; l.hi = split; r.lo = split; r.hi = nd.hi;
+    l.depth = r.depth = nd.depth + 1;
+    l.left = l.right = r.left = r.right = -1;
+    l.state = (l.hi - l.lo <= 3) ? ST_LEAF : ST_PENDING;
+    r.state = (r.hi - r.lo <= 3) ? ST_LEAF : ST_PENDING;
+    node_set_box(l, lbb[k]);
+    node_set_box(r, rbb[k]);
+    nodes[base] = l;
+    nodes[base + 1] = r;
+    const int np = (l.state == ST_PENDING) + (r.state == ST_PENDING);
+    if (np) atomicAdd(&ctr->n_pending, np);
+    nodes[v].state = ST_BRANCH; nodes[v].k = k; nodes[v].left = base; nodes[v].right = base + 1; nodes[v].split = split;
+    nodes[v].lmax = lmax[k]; nodes[v].rmin = rmin[k];
+}
+
+// "goes left" under its node's winning partition; 0 for items whose node did not split at this level
+__device__ __forceinline__ int goes_left(int p, int lvl_start, int lvl_end, const BNode* __restrict__ nodes, const int* __restrict__ idx,
+                                         const int* __restrict__ node_of, const double* __restrict__ mid,
+                                         const double* __restrict__ sa, int& v_out) {
+    const int v = node_of[p];
+    v_out = v;
+    if (v < lvl_start || v >= lvl_end) return -1;
+    const BNode& nd = nodes[v];
+    if (nd.state != ST_BRANCH) return -1;
+    const int i = idx[p];
+    const int k = nd.k;
+    if (k == 3) return sa[i] > nd.thresh ? 1 : 0;
+    return mid[3 * (size_t)i + k] < nd.mid[k] ? 1 : 0;
+}
+
+#define SCAN_ITEMS 4
+#define SCAN_THREADS 256
+#define SCAN_TILE (SCAN_ITEMS * SCAN_THREADS)
+// exclusive scan of the flags inside each 1024-item tile + the tile totals
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_local(int n, int lvl_start, int lvl_end, const BNode* __restrict__ nodes,
+                                                              const int* __restrict__ idx, const int* __restrict__ node_of,
+                                                              const double* __restrict__ mid, const double* __restrict__ sa,
+                                                              int* __restrict__ S, int* __restrict__ tile_sum) {
+    __shared__ int wsum[SCAN_THREADS / 32];
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int f[SCAN_ITEMS], tot = 0;
+    for (int j = 0; j < SCAN_ITEMS; j++) {
+        const int p = base + j;
+        int v;
+        f[j] = (p < n && goes_left(p, lvl_start, lvl_end, nodes, idx, node_of, mid, sa, v) == 1) ? 1 : 0;
+        tot += f[j];
+    }
+    int incl = tot;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    int woff = 0, all = 0;
+    for (int j = 0; j < SCAN_THREADS / 32; j++) { if (j < w) woff += wsum[j]; all += wsum[j]; }
+    int run = woff + incl - tot;
+    for (int j = 0; j < SCAN_ITEMS; j++) {
+        const int p = base + j;
+        if (p < n) S[p] = run;
+        run += f[j];
+    }
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = all;
+}
+// exclusive scan of the tile totals (one block)
+__global__ void __launch_bounds__(1024) k_scan_tiles(int ntiles, int* tile_sum) {
+    __shared__ int wsum[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < ntiles; base += 1024) {
+        const int t = base + threadIdx.x;
+        const int x = (t < ntiles) ? tile_sum[t] : 0;
+        int incl = x;
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        if (lane == 31) wsum[w] = incl;
+        __syncthreads();
+        int woff = 0, all = 0;
+        for (int j = 0; j < 32; j++) { if (j < w) woff += wsum[j]; all += wsum[j]; }
+        const int c = carry;
+        if (t < ntiles) tile_sum[t] = c + woff + incl - x;
+        __syncthreads();
+        if (threadIdx.x == 0) carry = c + all;
+        __syncthreads();
+    }
+}
+// stable partition of every node that split at this level
+__global__ void __launch_bounds__(256) k_scatter(int n, int lvl_start, int lvl_end, const BNode* __restrict__ nodes,
+                                                 const int* __restrict__ idx, const int* __restrict__ node_of,
+                                                 const double* __restrict__ mid, const double* __restrict__ sa,
+                                                 const int* __restrict__ S, const int* __restrict__ tile_off,
+                                                 int* __restrict__ idx2, int* __restrict__ node_of2) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    int v;
+    const int gl = goes_left(p, lvl_start, lvl_end, nodes, idx, node_of, mid, sa, v);
+    if (gl < 0) { idx2[p] = idx[p]; node_of2[p] = v; return; }
+    const BNode& nd = nodes[v];
+    const int lo = nd.lo;
+    const int before = (S[p] + tile_off[p / SCAN_TILE]) - (S[lo] + tile_off[lo / SCAN_TILE]);  // lefts in [lo, p)
+    int q, child;
+    if (gl) { q = lo + before; child = nd.left; }
+    else { q = nd.split + ((p - lo) - before); child = nd.right; }
+    idx2[q] = idx[p];
+    node_of2[q] = child;
+}
+
+// ---- numbering: bih_build() emits nodes in pre-order and leaves in traversal order ----
+__global__ void k_sizes(int lvl_start, int lvl_end, const BNode* __restrict__ nodes, int* nb, int* nl) {
+    int v = lvl_start + blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= lvl_end) return;
+    if (nodes[v].state == ST_BRANCH) {
+        nb[v] = 1 + nb[nodes[v].left] + nb[nodes[v].right];
+        nl[v] = nl[nodes[v].left] + nl[nodes[v].right];
+    } else { nb[v] = 0; nl[v] = 1; }
+}
+__global__ void k_number(int lvl_start, int lvl_end, const BNode* __restrict__ nodes, const int* __restrict__ nb,
+                         const int* __restrict__ nl, int* pre, int* lbase) {
+    int v = lvl_start + blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= lvl_end) return;
+    if (nodes[v].state != ST_BRANCH) return;
+    const int l = nodes[v].left, r = nodes[v].right;
+    pre[l] = pre[v] + 1; lbase[l] = lbase[v];
+    pre[r] = pre[v] + 1 + nb[l]; lbase[r] = lbase[v] + nl[l];
+}
+__global__ void k_emit(int n_nodes, const BNode* __restrict__ nodes, const int* __restrict__ pre, const int* __restrict__ lbase,
+                       GlomeBihNode* out_nodes, int* out_leaves) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes) return;
+    const BNode& nd = nodes[v];
+    if (nd.state == ST_BRANCH) {
+        GlomeBihNode o;
+        o.lsplit = nd.lmax + GLM_DELTA;  // Bih.hs:257-258
+        o.rsplit = nd.rmin - GLM_DELTA;
+        o.axis = (nd.k == 3) ? 0 : nd.k;
+        const int l = nd.left, r = nd.right;
+        o.left = (nodes[l].state == ST_BRANCH) ? pre[l] : ~lbase[l];
+        o.right = (nodes[r].state == ST_BRANCH) ? pre[r] : ~lbase[r];
+        o.pad = 0;
+        out_nodes[pre[v]] = o;
+    } else {
+        out_leaves[2 * lbase[v]] = nd.lo;
+        out_leaves[2 * lbase[v] + 1] = nd.hi - nd.lo;
+    }
+}
+
+struct DevMem {
+    std::vector<void*> ptrs;
+    ~DevMem() { for (void* p : ptrs) cudaFree(p); }
+    template <typename T> T* alloc(size_t count) {
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, (count ? count : 1) * sizeof(T));
+        if (e != cudaSuccess) throw BuildError(std::string("bih_build_gpu: cudaMalloc: ") + cudaGetErrorString(e));
+        ptrs.push_back(p);
+        return (T*)p;
+    }
+};
+
+static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+
+}  // namespace
+
+void bih_build_gpu(int64_t n64, const double* bboxes, int device, BihTree& out, double* timings_ms) {
+    if (n64 < 0 || n64 > 0x3fffffff) throw BuildError("bih_build_gpu: item count out of range");
+    const int n = (int)n64;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) throw BuildError("bih_build_gpu: no such CUDA device");
+    BK(cudaSetDevice(device));
+    out.nodes.clear(); out.leaves.clear(); out.order.clear();
+    if (n == 0) {  // bih [] : an empty leaf over the empty box (bih_build does the same)
+        out.bb = glm::empty_bbox();
+        out.leaves.push_back(0); out.leaves.push_back(0);
+        out.root = ~0;
+        if (timings_ms) timings_ms[0] = timings_ms[1] = timings_ms[2] = 0;
+        return;
+    }
+    DevMem M;
+    const int max_nodes = 3 * n + 4096;
+    double* d_bb = M.alloc<double>(6 * (size_t)n);
+    double* d_mid = M.alloc<double>(3 * (size_t)n);
+    double* d_sa = M.alloc<double>(n);
+    int* d_idx[2] = {M.alloc<int>(n), M.alloc<int>(n)};
+    int* d_nof[2] = {M.alloc<int>(n), M.alloc<int>(n)};
+    int* d_S = M.alloc<int>(n);
+    const int ntiles = cdiv(n, SCAN_TILE);
+    int* d_tiles = M.alloc<int>(ntiles);
+    BNode* d_nodes = M.alloc<BNode>(max_nodes);
+    LevelAcc* d_acc = M.alloc<LevelAcc>((size_t)n + 8);
+    Counters* d_ctr = M.alloc<Counters>(1);
+    unsigned long long* d_bbkeys = M.alloc<unsigned long long>(6);
+    double* d_bbout = M.alloc<double>(6);
+    cudaEvent_t ev[4];
+    for (auto& e : ev) BK(cudaEventCreate(&e));
+    struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int i = 0; i < 4; i++) cudaEventDestroy(e[i]); } } evg{ev};
+
+    BK(cudaEventRecord(ev[0]));
+    BK(cudaMemcpy(d_bb, bboxes, sizeof(double) * 6 * (size_t)n, cudaMemcpyHostToDevice));
+    BK(cudaEventRecord(ev[1]));
+    {   // bbox key seeds = empty_bbox (Vec.hs:706)
+        unsigned long long seeds[6];
+        // f2key on the host: same bit trick
+        auto hk = [](double x) { unsigned long long b; memcpy(&b, &x, 8); return (b >> 63) ? ~b : (b | 0x8000000000000000ull); };
+        for (int a = 0; a < 3; a++) { seeds[a] = hk(GLM_INFINITY); seeds[3 + a] = hk(-GLM_INFINITY); }
+        BK(cudaMemcpy(d_bbkeys, seeds, sizeof(seeds), cudaMemcpyHostToDevice));
+    }
+    k_prep<<<cdiv(n, 256), 256>>>(n, d_bb, d_mid, d_sa, d_idx[0], d_nof[0], d_bbkeys);
+    k_init_root<<<1, 1>>>(n, d_bbkeys, d_nodes, d_ctr, d_bbout);
+    BK(cudaGetLastError());
+
+    std::vector<std::pair<int, int>> levels;  // node id ranges
+    int lvl_start = 0, lvl_end = 1, cur = 0;
+    Counters hc;
+    BK(cudaMemcpy(&hc, d_ctr, sizeof(hc), cudaMemcpyDeviceToHost));
+    double hbb[6];
+    BK(cudaMemcpy(hbb, d_bbout, sizeof(hbb), cudaMemcpyDeviceToHost));
+    for (int a = 0; a < 3; a++)
+        if (hbb[a] == -GLM_INFINITY || hbb[3 + a] == GLM_INFINITY) throw BuildError("bih: infinite bounding box");  // Bih.hs:319-322
+    levels.push_back({0, 1});
+    while (hc.n_pending > 0) {
+        const int cnt = lvl_end - lvl_start;
+        BK(cudaMemsetAsync(&d_ctr->n_pending, 0, sizeof(int)));
+        k_acc_reset<<<cdiv(cnt, 256), 256>>>(cnt, d_acc);
+        k_accum<<<cdiv(n, 256), 256>>>(n, lvl_start, d_nodes, d_idx[cur], d_nof[cur], d_bb, d_mid, d_sa, d_acc);
+        k_decide<<<cdiv(cnt, 128), 128>>>(lvl_start, lvl_end, d_nodes, d_acc, d_ctr, max_nodes);
+        k_scan_local<<<ntiles, SCAN_THREADS>>>(n, lvl_start, lvl_end, d_nodes, d_idx[cur], d_nof[cur], d_mid, d_sa, d_S, d_tiles);
+        k_scan_tiles<<<1, 1024>>>(ntiles, d_tiles);
+        k_scatter<<<cdiv(n, 256), 256>>>(n, lvl_start, lvl_end, d_nodes, d_idx[cur], d_nof[cur], d_mid, d_sa, d_S, d_tiles,
+                                         d_idx[cur ^ 1], d_nof[cur ^ 1]);
+        BK(cudaGetLastError());
+        cur ^= 1;
+        BK(cudaMemcpy(&hc, d_ctr, sizeof(hc), cudaMemcpyDeviceToHost));
+        if (hc.err & ERR_DEPTH) throw BuildError("bih: recursion too deep (degenerate input)");
+        if (hc.err & ERR_NODES) throw BuildError("bih_build_gpu: node table overflow");
+        lvl_start = lvl_end;
+        lvl_end = hc.n_nodes;
+        if (lvl_end > lvl_start) levels.push_back({lvl_start, lvl_end});
+        if ((int)levels.size() > BUILD_MAX_DEPTH + 8) throw BuildError("bih: recursion too deep (degenerate input)");
+    }
+    const int n_nodes = hc.n_nodes;
+    int* d_nb = M.alloc<int>(n_nodes);
+    int* d_nl = M.alloc<int>(n_nodes);
+    int* d_pre = M.alloc<int>(n_nodes);
+    int* d_lbase = M.alloc<int>(n_nodes);
+    for (int L = (int)levels.size() - 1; L >= 0; L--) {
+        const int c = levels[L].second - levels[L].first;
+        k_sizes<<<cdiv(c, 256), 256>>>(levels[L].first, levels[L].second, d_nodes, d_nb, d_nl);
+    }
+    BK(cudaMemsetAsync(d_pre, 0, sizeof(int)));
+    BK(cudaMemsetAsync(d_lbase, 0, sizeof(int)));
+    for (size_t L = 0; L < levels.size(); L++) {
+        const int c = levels[L].second - levels[L].first;
+        k_number<<<cdiv(c, 256), 256>>>(levels[L].first, levels[L].second, d_nodes, d_nb, d_nl, d_pre, d_lbase);
+    }
+    int root_nb = 0, root_nl = 0;
+    BK(cudaMemcpy(&root_nb, d_nb, sizeof(int), cudaMemcpyDeviceToHost));
+    BK(cudaMemcpy(&root_nl, d_nl, sizeof(int), cudaMemcpyDeviceToHost));
+    GlomeBihNode* d_out_nodes = M.alloc<GlomeBihNode>(root_nb);
+    int* d_out_leaves = M.alloc<int>(2 * (size_t)root_nl);
+    k_emit<<<cdiv(n_nodes, 256), 256>>>(n_nodes, d_nodes, d_pre, d_lbase, d_out_nodes, d_out_leaves);
+    BK(cudaGetLastError());
+    BK(cudaEventRecord(ev[2]));
+    out.nodes.resize(root_nb);
+    out.leaves.resize(2 * (size_t)root_nl);
+    out.order.resize(n);
+    if (root_nb) BK(cudaMemcpy(out.nodes.data(), d_out_nodes, sizeof(GlomeBihNode) * (size_t)root_nb, cudaMemcpyDeviceToHost));
+    BK(cudaMemcpy(out.leaves.data(), d_out_leaves, sizeof(int) * 2 * (size_t)root_nl, cudaMemcpyDeviceToHost));
+    BK(cudaMemcpy(out.order.data(), d_idx[cur], sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost));
+    BK(cudaEventRecord(ev[3]));
+    BK(cudaEventSynchronize(ev[3]));
+    out.bb = mkbb(vec(hbb[0], hbb[1], hbb[2]), vec(hbb[3], hbb[4], hbb[5]));
+    out.root = (root_nb > 0) ? 0 : ~0;
+    if (timings_ms) {
+        float a = 0, b = 0, c = 0;
+        cudaEventElapsedTime(&a, ev[0], ev[1]);
+        cudaEventElapsedTime(&b, ev[1], ev[2]);
+        cudaEventElapsedTime(&c, ev[2], ev[3]);
+        timings_ms[0] = a; timings_ms[1] = b; timings_ms[2] = c;
+    }
+}
+
+}  // namespace glome_host

@@ -1,5 +1,7 @@
 // host_builder.cpp -- see host_builder.h.  Host code only (no CUDA); compiled -ffp-contract=off.
 #include "host_builder.h"
+#include "glome_build.h"
+#include <chrono>
 
 #include <algorithm>
 #include <cmath>
@@ -531,7 +533,10 @@ int Builder::bih(const std::vector<int32_t>& xs) {  // Bih.hs:309-324
         o[0] = b.p1.x; o[1] = b.p1.y; o[2] = b.p1.z; o[3] = b.p2.x; o[4] = b.p2.y; o[5] = b.p2.z;
     }
     bihs.emplace_back();
-    bih_build((int64_t)xs.size(), bbs.data(), bihs.back());
+    auto t0 = std::chrono::steady_clock::now();
+    if (build_device >= 0) bih_build_gpu((int64_t)xs.size(), bbs.data(), build_device, bihs.back(), build_ms);
+    else { bih_build((int64_t)xs.size(), bbs.data(), bihs.back()); build_ms[0] = build_ms[1] = build_ms[2] = 0; }
+    build_ms[3] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     Item it = mkitem(GLOME_BIH);
     it.ia = (int)bihs.size() - 1;
     it.kids = xs;

@@ -76,6 +76,8 @@ class Builder {
   public:
     std::vector<Item> items;
     std::vector<BihTree> bihs;
+    int build_device = -1;           // >= 0: `bih` builds its tree on that GPU (glome_build.cu), same result
+    double build_ms[4] = {0, 0, 0, 0}; // last bih: H2D, device build, D2H (GPU) or 0,0,0 + [3] host build wall ms
     std::vector<MeshData> meshes;
     std::vector<GlomeMaterial> materials;  // WARP a/b hold ITEM ids until flatten
     std::vector<GlomeTexture> textures;

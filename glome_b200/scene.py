@@ -119,6 +119,38 @@ class FlatView:
         self.max_depth = fs.max_depth
 
 
+BIH_NODE_DTYPE = np.dtype([("lsplit", "<f8"), ("rsplit", "<f8"), ("axis", "<i4"), ("left", "<i4"), ("right", "<i4"),
+                           ("pad", "<i4")])
+
+
+def bih_build(bboxes, device=None):
+    """The tree `bih` builds over objects with these bounding boxes (Bih.hs:211-324), as arrays:
+    nodes (pre-order GlomeBihNode records), leaves ({first, count} into order), order (the leaf-ordered
+    permutation), root ref, bb.  device=None: host builder; device=k: built on GPU k (same arrays), with
+    timings_ms = (H2D, device build, D2H)."""
+    lib = L.load()
+    bboxes = _f64(bboxes, (-1, 6))
+    nodes = C.POINTER(L.GlomeBihNode)()
+    leaves = C.POINTER(C.c_int32)()
+    order = C.POINTER(C.c_int32)()
+    nn, nl, root = C.c_int32(), C.c_int32(), C.c_int32()
+    bb = (C.c_double * 6)()
+    tm = (C.c_double * 3)()
+    if device is None:
+        L.check(lib.glome_bih_build(len(bboxes), _ptr(bboxes), C.byref(nodes), C.byref(nn), C.byref(leaves),
+                                    C.byref(nl), C.byref(order), C.byref(root), bb))
+    else:
+        L.check(lib.glome_bih_build_gpu(len(bboxes), _ptr(bboxes), int(device), C.byref(nodes), C.byref(nn),
+                                        C.byref(leaves), C.byref(nl), C.byref(order), C.byref(root), bb, tm))
+    res = dict(nodes=np.frombuffer(C.string_at(nodes, nn.value * 32), dtype=BIH_NODE_DTYPE).copy(),
+               leaves=np.frombuffer(C.string_at(leaves, nl.value * 8), dtype=np.int32).copy().reshape(-1, 2),
+               order=np.frombuffer(C.string_at(order, len(bboxes) * 4), dtype=np.int32).copy(), root=root.value,
+               bb=np.array(bb[:]), timings_ms=tuple(tm[:]))
+    for p in (nodes, leaves, order):
+        lib.glome_free(C.cast(p, C.c_void_p))
+    return res
+
+
 class SceneBuilder:
     """Host mirror of the GlomeTrace construction API.  Items are int ids."""
 
@@ -132,6 +164,16 @@ class SceneBuilder:
         if self.h:
             self.lib.glome_builder_destroy(self.h)
             self.h = None
+
+    def set_build_device(self, device):
+        """device >= 0: `bih` builds its tree on that GPU (same tree); -1: on the host (default)."""
+        L.check(self.lib.glome_builder_set_build_device(self.h, int(device)))
+
+    def last_build_ms(self):
+        """(H2D, device build, D2H, wall) of the last `bih`, milliseconds."""
+        out = (C.c_double * 4)()
+        L.check(self.lib.glome_builder_last_build_ms(self.h, out))
+        return tuple(out[:])
 
     def __del__(self):
         try:

@@ -310,6 +310,10 @@ typedef struct GlomeBuilder GlomeBuilder;
 
 int glome_builder_create(GlomeBuilder** out);
 int glome_builder_destroy(GlomeBuilder* b);
+/* device >= 0: `bih` (glome_sb_bih, the config scenes) builds its tree on that GPU; -1 (default): on the host.
+ * Same tree either way.  last_build_ms: the last bih's {H2D, device build, D2H, wall} in milliseconds. */
+int glome_builder_set_build_device(GlomeBuilder* b, int device);
+int glome_builder_last_build_ms(GlomeBuilder* b, double out[4]);
 
 /* constructors: return item id >= 0, or a negative error */
 int glome_sb_void(GlomeBuilder* b);
@@ -389,6 +393,12 @@ int glome_bih_build(int64_t n, const double* bboxes, GlomeBihNode** nodes_out, i
                     int32_t** leaves_out /* {first,count} pairs in item_order */, int32_t* n_leaves_out,
                     int32_t** item_order_out /* n: leaf-ordered permutation of 0..n-1 */,
                     int32_t* root_ref_out, double bb_out[6]);
+/* the same tree, built level by level on a GPU (glome_b200/csrc/glome_build.cu).
+ * Replaces build_rec's list recursion (Bih.hs:211-285); output arrays are identical to glome_bih_build's.
+ * timings_ms = {host->device, device build, device->host} or NULL.  GLOME_ENODEV without a device. */
+int glome_bih_build_gpu(int64_t n, const double* bboxes, int device, GlomeBihNode** nodes_out, int32_t* n_nodes_out,
+                        int32_t** leaves_out, int32_t* n_leaves_out, int32_t** item_order_out,
+                        int32_t* root_ref_out, double bb_out[6], double timings_ms[3]);
 /* mesh BVH (Mesh.hs:50-134): leafpool = {count, tri...} records, leafoff[leaf] = offset into leafpool */
 int glome_mesh_build(int64_t nverts, const double* verts, int64_t ntris, const int32_t* tris /*8 per tri*/,
                      GlomeBvhNode** nodes_out, int32_t* n_nodes_out, int32_t** leafpool_out,
