@@ -95,8 +95,10 @@ class ClockSampler:
         return out
 
 
-def build_scene(G):
+def build_scene(G, build_device=-1):
+    """build_device >= 0: the scene's `bih` is built on that GPU (glome_build.cu), -1: on the host; same tree."""
     b = G.SceneBuilder()
+    b.set_build_device(build_device)
     root, cam, recurs = b.config_scene(CONFIG, N_SPHERES, SEED)
     fs = b.flatten(root)
     return b, fs, cam, recurs
@@ -203,7 +205,19 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    b, fs, cam, recurs = build_scene(G)
+    # scene set-up (timed separately by the reference too, Glome.hs:448-453): the bih is built on this rank's GPU;
+    # rank 0 of a 1-GPU run also times the host builder on the same boxes for the report
+    setup = None
+    if rank == 0 and world == 1:
+        hb = build_scene(G)[0]
+        host_ms = hb.last_build_ms()[3]
+        hb.close()
+    b, fs, cam, recurs = build_scene(G, local_rank)
+    gm = b.last_build_ms()
+    if rank == 0 and world == 1:
+        setup = {"bih_items": N_SPHERES, "bih_build_gpu_ms": {"h2d": gm[0], "device": gm[1], "d2h": gm[2], "wall": gm[3]},
+                 "bih_build_host_ms": host_ms, "host_threads": os.cpu_count(),
+                 "note": "same tree either way (tests/test_gpu_build.py); not part of the timed frame"}
     scene = G.Scene(fs, local_rank)
     # N > 1: the gathered framebuffer is the packed 0x00RRGGBB image (what blitTile writes, Glome.hs:353-358)
     rdr = ShardedRenderer(scene, cam, WIDTH, HEIGHT, L.MODE_ONE_RAY, recurs, rank=rank, world=world, want_tcolor=False)
@@ -331,6 +345,8 @@ def main():
                          "note": "working set (~96 MB) is L2-resident: see profiles/ for L2 and issue-slot figures"},
             "wall_s_timed_region": t_wall,
         }
+        if setup:
+            line["scene_setup"] = setup
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             r = cpu_sample(G, fs, cam, recurs, 12.0, threads)
