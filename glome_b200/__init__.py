@@ -5,4 +5,4 @@ the ctypes plumbing tests and bench.py use.  Importing it never touches oracle/.
 """
 from . import _lib  # noqa: F401
 from .scene import (Scene, SceneBuilder, FlatView, camera, camera_rays, compose, deg, render_opts, rotate, scale,  # noqa: F401
-                    tile_rects, translate, HIT_DTYPE, bih_build)
+                    tile_rects, translate, HIT_DTYPE, bih_build, mesh_build)

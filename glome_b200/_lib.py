@@ -172,6 +172,8 @@ SIGNATURES = {
     "glome_bih_build_gpu": (C.c_int, [C.c_int64, _vp, C.c_int, _P(_P(GlomeBihNode)), _ip, _P(_ip), _ip, _P(_ip), _ip, _dp, _dp]),
     "glome_mesh_build": (C.c_int, [C.c_int64, _vp, C.c_int64, _vp, _P(_P(GlomeBvhNode)), _ip, _P(_ip), _ip,
                                    _P(_ip), _ip, _ip, _dp]),
+    "glome_mesh_build_gpu": (C.c_int, [C.c_int64, _vp, C.c_int64, _vp, C.c_int, _P(_P(GlomeBvhNode)), _ip, _P(_ip), _ip,
+                                       _P(_ip), _ip, _ip, _dp, _dp]),
     "glome_free": (None, [_vp]),
 }
 

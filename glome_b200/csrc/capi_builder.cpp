@@ -196,12 +196,30 @@ static int bih_build_any(int64_t n, const double* bboxes, int device, double* ti
         return GLOME_OK;
     } catch (const BuildError& e) { glome_set_error(e.msg); return GLOME_EBUILD; }
 }
+static int mesh_build_any(int64_t nverts, const double* verts, int64_t ntris, const int32_t* tris, int device, double* timings_ms,
+                          GlomeBvhNode** nodes_out, int32_t* n_nodes_out, int32_t** leafpool_out, int32_t* n_leafpool_out,
+                          int32_t** leafoff_out, int32_t* n_leaves_out, int32_t* root_ref_out, double bb_out[6]);
 int glome_mesh_build(int64_t nverts, const double* verts, int64_t ntris, const int32_t* tris, GlomeBvhNode** nodes_out,
                      int32_t* n_nodes_out, int32_t** leafpool_out, int32_t* n_leafpool_out, int32_t** leafoff_out,
                      int32_t* n_leaves_out, int32_t* root_ref_out, double bb_out[6]) {
+    return mesh_build_any(nverts, verts, ntris, tris, -1, nullptr, nodes_out, n_nodes_out, leafpool_out, n_leafpool_out, leafoff_out,
+                          n_leaves_out, root_ref_out, bb_out);
+}
+int glome_mesh_build_gpu(int64_t nverts, const double* verts, int64_t ntris, const int32_t* tris, int device,
+                         GlomeBvhNode** nodes_out, int32_t* n_nodes_out, int32_t** leafpool_out, int32_t* n_leafpool_out,
+                         int32_t** leafoff_out, int32_t* n_leaves_out, int32_t* root_ref_out, double bb_out[6],
+                         double timings_ms[3]) {
+    if (device < 0) { glome_set_error("glome_mesh_build_gpu needs a device index"); return GLOME_ENODEV; }
+    return mesh_build_any(nverts, verts, ntris, tris, device, timings_ms, nodes_out, n_nodes_out, leafpool_out, n_leafpool_out,
+                          leafoff_out, n_leaves_out, root_ref_out, bb_out);
+}
+static int mesh_build_any(int64_t nverts, const double* verts, int64_t ntris, const int32_t* tris, int device, double* timings_ms,
+                          GlomeBvhNode** nodes_out, int32_t* n_nodes_out, int32_t** leafpool_out, int32_t* n_leafpool_out,
+                          int32_t** leafoff_out, int32_t* n_leaves_out, int32_t* root_ref_out, double bb_out[6]) {
     try {
         MeshTree t;
-        mesh_build(nverts, verts, ntris, tris, t);
+        if (device >= 0) mesh_build_gpu(nverts, verts, ntris, tris, device, t, timings_ms);
+        else mesh_build(nverts, verts, ntris, tris, t);
         *n_nodes_out = (int32_t)t.nodes.size();
         *nodes_out = (GlomeBvhNode*)malloc(sizeof(GlomeBvhNode) * (t.nodes.size() + 1));
         memcpy(*nodes_out, t.nodes.data(), sizeof(GlomeBvhNode) * t.nodes.size());

@@ -11,4 +11,8 @@ namespace glome_host {
 // Throws BuildError (infinite bounding box, Bih.hs:319-322; recursion deeper than bih_build allows; no device).
 void bih_build_gpu(int64_t n, const double* bboxes, int device, BihTree& out, double* timings_ms);
 
+// mesh's BVH (Mesh.hs:50-134) the same way; identical to mesh_build()'s MeshTree.
+void mesh_build_gpu(int64_t nverts, const double* verts, int64_t ntris, const int32_t* tris, int device, MeshTree& out,
+                    double* timings_ms);
+
 }  // namespace glome_host

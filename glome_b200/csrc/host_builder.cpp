@@ -561,7 +561,10 @@ int Builder::mesh(int64_t nverts, const double* verts, int64_t nnorms, const dou
     m.tris.assign(tris, tris + 8 * ntris);
     if (ntexs) m.texs.assign(texs, texs + ntexs);
     if (ntags) m.tags.assign(tags, tags + ntags);
-    mesh_build(nverts, verts, ntris, tris, m.tree);
+    auto t0 = std::chrono::steady_clock::now();
+    if (build_device >= 0) mesh_build_gpu(nverts, verts, ntris, tris, build_device, m.tree, build_ms);
+    else { mesh_build(nverts, verts, ntris, tris, m.tree); build_ms[0] = build_ms[1] = build_ms[2] = 0; }
+    build_ms[3] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     Item it = mkitem(GLOME_MESH);
     it.ia = (int)meshes.size() - 1;
     return add(it);

@@ -151,6 +151,37 @@ def bih_build(bboxes, device=None):
     return res
 
 
+BVH_NODE_DTYPE = np.dtype([("lbb", "<f8", (6,)), ("rbb", "<f8", (6,)), ("left", "<i4"), ("right", "<i4"), ("pad", "<i4", (6,))])
+
+
+def mesh_build(verts, tris, device=None):
+    """The BVH `mesh` builds (Mesh.hs:50-134): nodes (pre-order GlomeBvhNode), leafpool ({count, tri...} records),
+    leafoff (leaf -> offset), root ref, bb.  tris = n x 8 int32 {a,b,c,na,nb,nc,tex,tag}.  device as in bih_build."""
+    lib = L.load()
+    verts = _f64(verts, (-1, 3))
+    tris = _i32(tris).reshape(-1, 8)
+    nodes = C.POINTER(L.GlomeBvhNode)()
+    leafpool = C.POINTER(C.c_int32)()
+    leafoff = C.POINTER(C.c_int32)()
+    nn, nlp, nl, root = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+    bb = (C.c_double * 6)()
+    tm = (C.c_double * 3)()
+    if device is None:
+        L.check(lib.glome_mesh_build(len(verts), _ptr(verts), len(tris), _ptr(tris), C.byref(nodes), C.byref(nn),
+                                     C.byref(leafpool), C.byref(nlp), C.byref(leafoff), C.byref(nl), C.byref(root), bb))
+    else:
+        L.check(lib.glome_mesh_build_gpu(len(verts), _ptr(verts), len(tris), _ptr(tris), int(device), C.byref(nodes),
+                                         C.byref(nn), C.byref(leafpool), C.byref(nlp), C.byref(leafoff), C.byref(nl),
+                                         C.byref(root), bb, tm))
+    res = dict(nodes=np.frombuffer(C.string_at(nodes, nn.value * 128), dtype=BVH_NODE_DTYPE).copy(),
+               leafpool=np.frombuffer(C.string_at(leafpool, nlp.value * 4), dtype=np.int32).copy(),
+               leafoff=np.frombuffer(C.string_at(leafoff, nl.value * 4), dtype=np.int32).copy(), root=root.value,
+               bb=np.array(bb[:]), timings_ms=tuple(tm[:]))
+    for p in (nodes, leafpool, leafoff):
+        lib.glome_free(C.cast(p, C.c_void_p))
+    return res
+
+
 class SceneBuilder:
     """Host mirror of the GlomeTrace construction API.  Items are int ids."""
 

@@ -310,8 +310,8 @@ typedef struct GlomeBuilder GlomeBuilder;
 
 int glome_builder_create(GlomeBuilder** out);
 int glome_builder_destroy(GlomeBuilder* b);
-/* device >= 0: `bih` (glome_sb_bih, the config scenes) builds its tree on that GPU; -1 (default): on the host.
- * Same tree either way.  last_build_ms: the last bih's {H2D, device build, D2H, wall} in milliseconds. */
+/* device >= 0: `bih` and `mesh` (glome_sb_bih, glome_sb_mesh, the config scenes) build their trees on that GPU; -1 (default): on the host.
+ * Same tree either way.  last_build_ms: the last bih's / mesh's {H2D, device build, D2H, wall} in milliseconds. */
 int glome_builder_set_build_device(GlomeBuilder* b, int device);
 int glome_builder_last_build_ms(GlomeBuilder* b, double out[4]);
 
@@ -404,6 +404,11 @@ int glome_mesh_build(int64_t nverts, const double* verts, int64_t ntris, const i
                      GlomeBvhNode** nodes_out, int32_t* n_nodes_out, int32_t** leafpool_out,
                      int32_t* n_leafpool_out, int32_t** leafoff_out, int32_t* n_leaves_out,
                      int32_t* root_ref_out, double bb_out[6]);
+/* the same BVH built on a GPU (glome_build.cu); replaces build_tree's list recursion (Mesh.hs:69-113) */
+int glome_mesh_build_gpu(int64_t nverts, const double* verts, int64_t ntris, const int32_t* tris /*8 per tri*/, int device,
+                         GlomeBvhNode** nodes_out, int32_t* n_nodes_out, int32_t** leafpool_out,
+                         int32_t* n_leafpool_out, int32_t** leafoff_out, int32_t* n_leaves_out,
+                         int32_t* root_ref_out, double bb_out[6], double timings_ms[3]);
 void glome_free(void* p);
 
 #ifdef __cplusplus

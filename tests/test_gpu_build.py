@@ -92,3 +92,57 @@ def test_scene_built_on_gpu_is_the_same_flat_scene_and_frame():
             ms = b.last_build_ms()
             assert ms[1] > 0  # device build time was recorded
     assert frames[0] == frames[1]
+
+
+def grid_mesh(nx, ny, seed):
+    """height-field grid: (nx+1)*(ny+1) shared vertices, 2*nx*ny triangles (config 3's shape)"""
+    rng = np.random.default_rng(seed)
+    xs, ys = np.meshgrid(np.arange(nx + 1.0), np.arange(ny + 1.0), indexing="ij")
+    verts = np.stack([xs, rng.uniform(0, 2, xs.shape), ys], -1).reshape(-1, 3)
+    i, j = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+    a = (i * (ny + 1) + j).ravel(); b = a + 1; c = a + (ny + 1); d = c + 1
+    t = np.concatenate([np.stack([a, b, c], -1), np.stack([b, d, c], -1)])
+    tris = np.full((len(t), 8), -1, dtype=np.int32)
+    tris[:, :3] = t
+    return verts, tris
+
+
+def same_mesh_tree(a, b):
+    assert a["root"] == b["root"]
+    assert np.array_equal(a["bb"], b["bb"])
+    assert np.array_equal(a["leafoff"], b["leafoff"])
+    assert np.array_equal(a["leafpool"], b["leafpool"])
+    assert a["nodes"].tobytes() == b["nodes"].tobytes()
+
+
+@pytest.mark.parametrize("nx,ny,seed", [(1, 1, 1), (2, 1, 2), (7, 5, 3), (60, 40, 4), (300, 200, 5)])
+def test_gpu_mesh_bvh_equals_host_and_oracle(nx, ny, seed):
+    verts, tris = grid_mesh(nx, ny, seed)
+    g = G.mesh_build(verts, tris, device=0)
+    same_mesh_tree(g, G.mesh_build(verts, tris))
+    if len(tris) <= 5000:
+        o = O.mesh_build(verts, tris)
+        assert g["nodes"].tobytes() == o["nodes"].tobytes() and np.array_equal(g["leafpool"], o["leafpool"])
+
+
+def test_gpu_mesh_bvh_full_size_config3_and_soup():
+    verts, tris = grid_mesh(1000, 1000, 3)  # 2 000 000 triangles
+    g = G.mesh_build(verts, tris, device=0)
+    same_mesh_tree(g, G.mesh_build(verts, tris))
+    rng = np.random.default_rng(9)     # triangle soup: random sizes, so the big/small partition fires
+    v = rng.uniform(-50, 50, (30000, 3))
+    v[::7] *= 3
+    t = np.full((10000, 8), -1, dtype=np.int32)
+    t[:, :3] = rng.permutation(30000).reshape(-1, 3)
+    same_mesh_tree(G.mesh_build(v, t, device=0), G.mesh_build(v, t))
+
+
+def test_mesh_scene_built_on_gpu_is_the_same_flat_scene():
+    sigs = []
+    for dev in (-1, 0):
+        b = G.SceneBuilder()
+        b.set_build_device(dev)
+        root, cam, rec = b.config_scene(3, 20000)
+        fv = G.FlatView(b.flatten(root))
+        sigs.append(hashlib.sha1(fv.bvhnodes.tobytes() + fv.bihnodes.tobytes() + fv.ipool.tobytes() + fv.dpool.tobytes()).hexdigest())
+    assert sigs[0] == sigs[1]
