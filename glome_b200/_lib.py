@@ -109,6 +109,8 @@ SIGNATURES = {
     "glome_render_dev": (C.c_int, [_vp, _P(GlomeCamera), C.c_int, C.c_int, _P(GlomeRenderOpts), _vp, _vp,
                                    _P(GlomeRenderStats), _vp]),
     "glome_scene_launches": (C.c_int64, [_vp]),
+    "glome_get_tags": (C.c_int, [_vp, _P(GlomeCamera), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, C.c_int, _ip, _ip,
+                                 _P(GlomeHit)]),
     "glome_dev_alloc": (C.c_int, [C.c_int, C.c_int64, _P(_vp)]),
     "glome_dev_free": (C.c_int, [C.c_int, _vp]),
     "glome_render_opts_default": (None, [_P(GlomeRenderOpts)]),
@@ -168,6 +170,7 @@ SIGNATURES = {
     "glome_camera": (C.c_int, [_dp, _dp, _dp, C.c_double, _P(GlomeCamera)]),
     "glome_sb_flatten": (C.c_int, [_vp, C.c_int, _P(GlomeFlatScene)]),
     "glome_sb_config_scene": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_uint64, _P(GlomeCamera), _ip]),
+    "glome_sb_load_nff": (C.c_int, [_vp, C.c_char_p, C.c_int64, _P(GlomeCamera), _dp, _P(C.c_int64)]),
     "glome_bih_build": (C.c_int, [C.c_int64, _vp, _P(_P(GlomeBihNode)), _ip, _P(_ip), _ip, _P(_ip), _ip, _dp]),
     "glome_bih_build_gpu": (C.c_int, [C.c_int64, _vp, C.c_int, _P(_P(GlomeBihNode)), _ip, _P(_ip), _ip, _P(_ip), _ip, _dp, _dp]),
     "glome_mesh_build": (C.c_int, [C.c_int64, _vp, C.c_int64, _vp, _P(_P(GlomeBvhNode)), _ip, _P(_ip), _ip,

@@ -165,6 +165,10 @@ int glome_sb_config_scene(GlomeBuilder* b, int config, int64_t n, uint64_t seed,
 static int bih_build_any(int64_t n, const double* bboxes, int device, double* timings_ms, GlomeBihNode** nodes_out,
                          int32_t* n_nodes_out, int32_t** leaves_out, int32_t* n_leaves_out, int32_t** item_order_out,
                          int32_t* root_ref_out, double bb_out[6]);
+int glome_sb_load_nff(GlomeBuilder* b, const char* text, int64_t len, GlomeCamera* cam, double bg[3], int64_t* consumed) {
+    if (!b || !text) return GLOME_EINVAL;
+    GUARD(nff_load(b->b, text, len, cam, bg, consumed));
+}
 int glome_bih_build(int64_t n, const double* bboxes, GlomeBihNode** nodes_out, int32_t* n_nodes_out, int32_t** leaves_out,
                     int32_t* n_leaves_out, int32_t** item_order_out, int32_t* root_ref_out, double bb_out[6]) {
     return bih_build_any(n, bboxes, -1, nullptr, nodes_out, n_nodes_out, leaves_out, n_leaves_out, item_order_out, root_ref_out, bb_out);

@@ -156,5 +156,8 @@ class Builder {
 // BASELINE.json config scenes (scenes.cpp)
 int config_scene(Builder& b, int config, int64_t n, uint64_t seed, GlomeCamera* cam, int* recurs);
 void make_camera(const Vec& pos, const Vec& at, const Vec& up, Flt angle, GlomeCamera* out);  // Scene.hs:48
+// NFF / SPD scene text -> items, lights and camera (Spd.hs:1-261; nff.cpp).  Returns the scene's root item
+// (bih of the fill groups); consumed = bytes parsed before the reader stopped.
+int nff_load(Builder& b, const char* text, int64_t len, GlomeCamera* cam, double bg[3], int64_t* consumed);
 
 }  // namespace glome_host

@@ -200,6 +200,16 @@ class SceneBuilder:
         """device >= 0: `bih` builds its tree on that GPU (same tree); -1: on the host (default)."""
         L.check(self.lib.glome_builder_set_build_device(self.h, int(device)))
 
+    def load_nff(self, text):
+        """Spd.hs:1-261: NFF / SPD scene text -> (root item, camera, background rgb, bytes consumed)."""
+        if isinstance(text, str):
+            text = text.encode("ascii")
+        cam = L.GlomeCamera()
+        bg = (C.c_double * 3)()
+        used = C.c_int64()
+        root = L.check(self.lib.glome_sb_load_nff(self.h, text, len(text), C.byref(cam), bg, C.byref(used)))
+        return root, cam, tuple(bg[:]), used.value
+
     def last_build_ms(self):
         """(H2D, device build, D2H, wall) of the last `bih`, milliseconds."""
         out = (C.c_double * 4)()
@@ -428,6 +438,15 @@ class Scene:
         L.check(self.lib.glome_trace_batch(self.h, len(rays), _ptr(rays), _ptr(t), stride, int(recurs), _ptr(rgba),
                                            _ptr(depth), _ptr(hits) if want_hits else None))
         return (rgba, depth, hits) if want_hits else (rgba, depth)
+
+    def get_tags(self, cam, width, height, px, py, recurs=3):
+        """getTags' (Glome.hs:410-414): (tag ids of the object under the pixel, partial flag, primary hit record)."""
+        tags = (C.c_int32 * L.GLOME_MAX_STACK)()
+        n, partial = C.c_int32(), C.c_int32()
+        hit = L.GlomeHit()
+        L.check(self.lib.glome_get_tags(self.h, C.byref(cam), width, height, px, py, recurs, tags, L.GLOME_MAX_STACK,
+                                        C.byref(n), C.byref(partial), C.byref(hit)))
+        return list(tags[:min(n.value, L.GLOME_MAX_STACK)]), bool(partial.value), hit
 
     def render(self, cam, width, height, opts=None, want_rgb8=False, out=None, rgb8_out=None):
         """renderTiles: returns (tcolor[h,w,5], rgb8[h,w] or None, stats)."""

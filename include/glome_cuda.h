@@ -263,6 +263,12 @@ int glome_inside_batch(GlomeScene* s, int64_t n, const double* pts, uint8_t* ins
  * rgba = n*4 doubles (ColorA, not premultiplied), depth = n doubles (ridepth of the primary hit). */
 int glome_trace_batch(GlomeScene* s, int64_t n, const double* rays, const double* tmax,
                       int tmax_stride, int recurs, double* rgba, double* depth, GlomeHit* hits_or_null);
+/* getTags' / get_tags (Glome.hs:69-72, 410-414): the tags of the object under pixel (px, py), what GlomeView prints
+ * on a click.  tags receives min(*ntags, max_tags) ids, head (innermost) first.  *partial = 1 when the hit's textures
+ * can yield Reflect / Refract / Warp materials: the reference then prepends the tags gathered by those recursive
+ * traces, which the device does not materialise.  hit_out (optional) is the primary Rayint. */
+int glome_get_tags(GlomeScene* s, const GlomeCamera* cam, int width, int height, int px, int py, int recurs,
+                   int32_t* tags, int max_tags, int* ntags, int* partial, GlomeHit* hit_out);
 /* renderTiles (+ blitTile)  (Glome.hs:379-386, 353-358).  tcolor = w*h*5 doubles (r,g,b,a,depth),
  * row-major, or NULL when only the packed image is wanted; rgb8 = w*h uint32 or NULL.  Pixels of tiles not selected by tile_first/tile_stride are
  * left untouched. */
@@ -385,6 +391,13 @@ int glome_sb_flatten(GlomeBuilder* b, int root, GlomeFlatScene* out);
  *   4: CSG-heavy grid                            (5 = scene 3, rendered with adaptive AA) */
 int glome_sb_config_scene(GlomeBuilder* b, int config, int64_t n, uint64_t seed, GlomeCamera* cam,
                           int* recurs_out);
+
+/* NFF (Neutral File Format, the SPD benchmark scenes) reader: Spd.hs:1-261, quirks included (groups and lights end
+ * up in reverse file order, the last camera / background win, a "#" comment ends the scene; see nff.cpp).
+ * Adds the scene's items, materials and lights to the builder and returns the root item
+ * (`bih` of one `tex (bih prims) fill` per "f" group); cam / bg (3 doubles) / consumed (bytes parsed) may be NULL.
+ * len < 0: text is NUL-terminated.  GLOME_EBUILD when the text has no camera or no background. */
+int glome_sb_load_nff(GlomeBuilder* b, const char* text, int64_t len, GlomeCamera* cam, double bg[3], int64_t* consumed);
 
 /* Tree builders on their own (host, multi-threaded): used by glome_sb_bih / glome_sb_mesh and
  * compared against the oracle's literal restatement in tests.

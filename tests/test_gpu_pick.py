@@ -1,0 +1,35 @@
+"""getTags' (Glome.hs:410-414): clicking a pixel returns the tag list of the trace result.  The device returns the
+primary hit's own tag stack; the reference's list is `ts ++ tags` where ts comes from Reflect / Refract / Warp
+recursion, so for hits flagged `partial` the device list must be the SUFFIX of the oracle's list, otherwise equal."""
+import numpy as np
+import pytest
+
+import glome_b200 as G
+from glome_b200 import _lib as L
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def test_get_tags_matches_the_oracle_on_testscene():
+    b = G.SceneBuilder()
+    root, cam, rec = b.config_scene(1, 0)
+    fs = b.flatten(root)
+    gs, osc = G.Scene(fs, 0), O.OracleScene(fs)
+    w, h = 180, 120
+    xs, ys = np.meshgrid(np.arange(3, w, 7), np.arange(2, h, 5))
+    xs, ys = xs.ravel(), ys.ravel()
+    rays = G.camera_rays(cam, w, h, xs, ys)
+    _, _, ohits, otags = osc.trace(rays, recurs=rec, want_hits=True, want_tags=True)
+    n_tagged = n_partial = 0
+    for i, (x, y) in enumerate(zip(xs, ys)):
+        tags, partial, hit = gs.get_tags(cam, w, h, int(x), int(y), rec)
+        ref = list(otags[i, 1:1 + min(otags[i, 0], 16)])
+        assert hit.hit == ohits["hit"][i] and hit.prim == ohits["prim"][i]
+        if partial:
+            n_partial += 1
+            assert ref[len(ref) - len(tags):] == tags if tags else True
+        else:
+            assert tags == ref
+        n_tagged += bool(tags)
+    assert n_tagged > 20 and n_partial > 0  # the scene has tagged objects and mirror / warp surfaces
