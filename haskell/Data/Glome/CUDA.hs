@@ -47,6 +47,12 @@ foreign import ccall safe   "glome_shadow_batch"   c_shadow_batch   :: Ptr Glome
 foreign import ccall safe   "glome_trace_batch"    c_trace_batch    :: Ptr GlomeSceneH -> Int64 -> Ptr CDouble -> Ptr CDouble -> CInt -> CInt -> Ptr CDouble -> Ptr CDouble -> Ptr CudaHit -> IO CInt
 foreign import ccall unsafe "glome_last_error"     c_last_error     :: IO CString
 foreign import ccall unsafe "glome_render_opts_default" c_opts_default :: Ptr RenderOptsC -> IO ()
+-- getTags' (Glome.hs:410-414): tags of the object under a pixel
+foreign import ccall safe   "glome_get_tags"       c_get_tags       :: Ptr GlomeSceneH -> Ptr CDouble -> CInt -> CInt -> CInt -> CInt -> CInt -> Ptr Int32 -> CInt -> Ptr CInt -> Ptr CInt -> Ptr CudaHit -> IO CInt
+-- scene set-up on the GPU: the trees of `bih` / `mesh` (Bih.hs:211-285, Mesh.hs:69-113), same arrays as the host builders
+foreign import ccall safe   "glome_builder_set_build_device" c_builder_set_build_device :: Ptr GlomeBuilderH -> CInt -> IO CInt
+-- NFF / SPD scene text (Spd.hs)
+foreign import ccall safe   "glome_sb_load_nff"    c_sb_load_nff    :: Ptr GlomeBuilderH -> CString -> Int64 -> Ptr CDouble -> Ptr CDouble -> Ptr Int64 -> IO CInt
 
 foreign import ccall unsafe "glome_builder_create"  c_builder_create  :: Ptr (Ptr GlomeBuilderH) -> IO CInt
 foreign import ccall unsafe "glome_builder_destroy" c_builder_destroy :: Ptr GlomeBuilderH -> IO CInt
