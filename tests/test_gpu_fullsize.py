@@ -105,3 +105,45 @@ def test_config4_csg_reflection_depth():
     bad = d.max(-1) > 1e-6
     assert bad.mean() <= 1e-4, "%d pixels differ" % int(bad.sum())
     assert rec == 5 and st.rays_secondary > 0 and st.overflow_rays == 0
+
+
+def test_repeated_frames_are_bit_identical_with_lane_donation():
+    """The traversal kernels hand subtrees of one ray to idle lanes of the warp (drain phase) and take their
+    batches from an atomic counter: the frame must not depend on who walked what.  Small frames are the ones
+    where donation does most of the work; the big one checks the steady state."""
+    b = G.SceneBuilder()
+    root, cam, rec = b.config_scene(2, 1000000)
+    gs = G.Scene(b.flatten(root))
+    for w, h, mode, reps in ((32, 16, L.MODE_ONE_RAY, 12), (160, 90, L.MODE_ADAPTIVE_AA, 6), (720, 480, L.MODE_ADAPTIVE_AA, 3),
+                             (1920, 1080, L.MODE_ONE_RAY, 3)):
+        opts = G.render_opts(mode=mode, recurs=rec)
+        first = gs.render(cam, w, h, opts)[0].tobytes()
+        for _ in range(reps):
+            assert gs.render(cam, w, h, opts)[0].tobytes() == first
+
+
+def test_small_frames_of_the_big_cloud_match_the_oracle():
+    """Frames with far fewer rays than lane slots (every lane donates or steals) against the oracle, all pixels."""
+    b = G.SceneBuilder()
+    root, cam, rec = b.config_scene(2, 1000000)
+    fs = b.flatten(root)
+    gs, osc = G.Scene(fs), O.OracleScene(fs)
+    for w, h, mode in ((32, 16, L.MODE_ONE_RAY), (130, 70, L.MODE_ONE_RAY), (160, 90, L.MODE_ADAPTIVE_AA)):
+        opts = G.render_opts(mode=mode, recurs=rec)
+        tg, _, st = gs.render(cam, w, h, opts)
+        to, _ = osc.render(cam, w, h, opts)
+        assert np.array_equal(tg, to)
+        assert st.overflow_rays == 0
+
+
+def test_shadow_agrees_with_rayint_where_the_reference_says_so():
+    """Solid.hs:218-221: the default `shadow` is `rayint` reduced to a Bool, and Sphere's own shadow test answers the
+    same question, so on a bih of spheres shadow r d == hit (rayint r d) for every ray (a size-independent property)."""
+    b = G.SceneBuilder()
+    root, cam, rec = b.config_scene(2, 1000000)
+    gs = G.Scene(b.flatten(root))
+    ys, xs = np.mgrid[0:1080:5, 0:1920:5]
+    rays = G.camera_rays(cam, 1920, 1080, xs.ravel(), ys.ravel())
+    for d in (1000000.0, 150.0, 40.0):
+        hit = gs.rayint(rays, d)["hit"] != 0
+        assert np.array_equal(gs.shadow(rays, d).astype(bool), hit)
