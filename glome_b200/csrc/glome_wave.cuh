@@ -160,6 +160,9 @@ __device__ __forceinline__ bool unwrap_prim(const DScene& S, int ni, GlomeNode& 
 #ifndef GW_REFILL_MIN
 #define GW_REFILL_MIN 8
 #endif
+#ifndef GW_BVH_MINBLOCKS
+#define GW_BVH_MINBLOCKS 6  /* 80 regs, 24 warps/SM: 3 % over 3 blocks (106 regs); the kernel is bound by its ~200 instructions per two-box node, not by occupancy */
+#endif
 #ifndef GW_GUIDED
 #define GW_GUIDED 1  /* guided self-scheduling of the sample list */
 #endif
@@ -508,7 +511,7 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScen
 // K1 for a Mesh segment (rayint_mesh, Mesh.hs:136-198): persistent, per-lane refill.
 // A Mesh casts no shadows (Mesh.hs:210), so there is no any-hit variant.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 3) k_bvh_closest(DScene S, WaveParams P, int segidx, Seg seg, unsigned int* counter) {
+__global__ void __launch_bounds__(128, GW_BVH_MINBLOCKS) k_bvh_closest(DScene S, WaveParams P, int segidx, Seg seg, unsigned int* counter) {
     const unsigned int FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const GlomeNode mn = S.nodes[seg.node];
