@@ -77,7 +77,7 @@ class GlomeCamera(C.Structure):
 class GlomeRenderOpts(C.Structure):
     _fields_ = [("mode", C.c_int32), ("blocksize", C.c_int32), ("recurs", C.c_int32), ("tint_depth", C.c_int32),
                 ("thresholds", C.c_double * 4), ("tile_first", C.c_int32), ("tile_stride", C.c_int32),
-                ("want_rgb8", C.c_int32), ("reserved", C.c_int32)]
+                ("want_rgb8", C.c_int32), ("debug_heatmap", C.c_int32)]
 
 
 class GlomeRenderStats(C.Structure):
@@ -109,6 +109,7 @@ SIGNATURES = {
     "glome_render_dev": (C.c_int, [_vp, _P(GlomeCamera), C.c_int, C.c_int, _P(GlomeRenderOpts), _vp, _vp,
                                    _P(GlomeRenderStats), _vp]),
     "glome_scene_launches": (C.c_int64, [_vp]),
+    "glome_debug_count_batch": (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_int, _vp]),
     "glome_get_tags": (C.c_int, [_vp, _P(GlomeCamera), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, C.c_int, _ip, _ip,
                                  _P(GlomeHit)]),
     "glome_dev_alloc": (C.c_int, [C.c_int, C.c_int64, _P(_vp)]),

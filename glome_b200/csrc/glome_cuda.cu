@@ -805,6 +805,46 @@ extern "C" int glome_get_tags(GlomeScene* s, const GlomeCamera* cam, int width, 
     return GLOME_OK;
 }
 
+// rayint_debug's count per ray (Solid.hs:155; Bih.hs:378-412) and get_color_debug's tint (Glome.hs:57-60)
+__global__ void k_debug_count_batch(DScene S, long long n, const double* __restrict__ rays, const double* __restrict__ tmax,
+                                    int stride, int* __restrict__ out) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Ray r = mkray(vec(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]), vec(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]));
+    out[i] = debug_count_node(S, S.root, r, tmax[stride ? i : 0]);
+}
+__global__ void k_debug_tint(DScene S, TileGeom g, DCamera cam, int tile_first, int tile_stride, double* __restrict__ out) {
+    long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (pix >= (long long)g.width * g.height) return;
+    int x = (int)(pix % g.width), y = (int)(pix / g.width);
+    int ti = (x / g.bs) * g.nty + (y / g.bs);  // renderTiles enumerates tiles x-major (Glome.hs:371-377)
+    if (ti % tile_stride != tile_first) return;
+    Flt xc, yc;
+    getCoordsf(g.width, g.height, (Flt)x, (Flt)y, xc, yc);
+    int dbg = debug_count_node(S, S.root, camera_ray(cam, xc, yc), GLM_INFINITY);
+    out[5 * pix] = ((Flt)(dbg % 30) / 60) + out[5 * pix];
+    out[5 * pix + 1] = out[5 * pix + 1] + ((Flt)dbg / 1000);
+}
+extern "C" int glome_debug_count_batch(GlomeScene* s, int64_t n, const double* rays, const double* tmax, int tmax_stride,
+                                       int32_t* counts) {
+    if (!s || n < 0 || !rays || !tmax || !counts) { g_err = "bad argument"; return GLOME_EINVAL; }
+    if (n == 0) return GLOME_OK;
+    CK(cudaSetDevice(s->device));
+    int rc;
+    size_t nt = tmax_stride ? (size_t)n : 1;
+    if ((rc = grow(s, 0, (size_t)n * 48))) return rc;
+    if ((rc = grow(s, 1, nt * 8))) return rc;
+    if ((rc = grow(s, 2, (size_t)n * 4))) return rc;
+    CK(cudaMemcpy(s->bw[0], rays, (size_t)n * 48, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->bw[1], tmax, nt * 8, cudaMemcpyHostToDevice));
+    k_debug_count_batch<<<(unsigned)((n + 63) / 64), 64>>>(s->d, n, (const double*)s->bw[0], (const double*)s->bw[1], tmax_stride,
+                                                           (int*)s->bw[2]);
+    s->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(counts, s->bw[2], (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return GLOME_OK;
+}
+
 extern "C" void glome_render_opts_default(GlomeRenderOpts* o) {
     memset(o, 0, sizeof(*o));
     o->mode = GLOME_MODE_ADAPTIVE_AA;  // the live path of the reference (Glome.hs:385)
@@ -812,7 +852,7 @@ extern "C" void glome_render_opts_default(GlomeRenderOpts* o) {
     o->recurs = 3;                     // Glome.hs:25
     o->tint_depth = 0;
     o->thresholds[0] = 0.14; o->thresholds[1] = 0.15; o->thresholds[2] = 0.16; o->thresholds[3] = 0.18;  // Glome.hs:221-224
-    o->tile_first = 0; o->tile_stride = 1; o->want_rgb8 = 0;
+    o->tile_first = 0; o->tile_stride = 1; o->want_rgb8 = 0; o->debug_heatmap = 0;
 }
 
 extern "C" int glome_tile_count(int width, int height, int blocksize) {
@@ -963,6 +1003,10 @@ extern "C" int glome_render_dev(GlomeScene* s, const GlomeCamera* cam, int width
                                 double* tcolor_dev, uint32_t* rgb8_dev, GlomeRenderStats* stats, void* stream) {
     if (!s || !cam || !o || !tcolor_dev || width <= 0 || height <= 0 || o->blocksize <= 0 || o->tile_stride <= 0 ||
         o->tile_first < 0 || o->tile_first >= o->tile_stride) { g_err = "bad argument"; return GLOME_EINVAL; }
+    if (o->debug_heatmap && (o->mode != GLOME_MODE_ONE_RAY || o->tint_depth)) {
+        g_err = "debug_heatmap is get_color_debug per pixel (Glome.hs:57-60): GLOME_MODE_ONE_RAY without tint_depth only";
+        return GLOME_EINVAL;
+    }
     CK(cudaSetDevice(s->device));
     cudaStream_t st = (cudaStream_t)stream;
     TileGeom g = make_geom(width, height, o->blocksize);
@@ -1005,6 +1049,11 @@ extern "C" int glome_render_dev(GlomeScene* s, const GlomeCamera* cam, int width
                 W.mode = 0; W.out = tcolor_dev;
                 if ((rc = launch_wave(s, W, (long long)n_sel * g.slots_per_tile, st))) return rc;
             } else if ((rc = launch_trace_c<0>(s, P, st))) return rc;
+            if (o->debug_heatmap) {
+                k_debug_tint<<<(unsigned)((npix + 63) / 64), 64, 0, st>>>(s->d, g, P.cam, o->tile_first, o->tile_stride, tcolor_dev);
+                s->launches++;
+                CK(cudaGetLastError());
+            }
         } else {
             // workspace: v (pass 1-4 samples), ray queue
             if (s->ws_pix < npix) {

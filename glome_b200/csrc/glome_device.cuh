@@ -1463,6 +1463,81 @@ __device__ void trace(const DScene& S, int lightset, int sld, const Ray& ray, Fl
 // ---------------------------------------------------------------------------------------------
 // Glome.hs: camera rays
 // ---------------------------------------------------------------------------------------------
+// ---- rayint_debug: the Int half of (Rayint, Int) (get_color_debug's heat map, Glome.hs:57-60) --------------
+// The count does not depend on what is hit.  Bih: +1 per branch entered on the reference's own (unculled,
+// unclamped) walk, leaves get `fmin d far` (Bih.hs:378-412); [s]: sum (Solid.hs:312,329); Instance: transformed
+// ray, d * lenscale (Solid.hs:447-461); Bound: +1 when the gate passes (Bound.hs:37-42); InnerBound: sb
+// (Bound.hs:107); Tag / Tex / NoShadow pass through, OnlyShadow is 0 (Tex.hs:55,67,79,90); everything else is the
+// class default 0 (Solid.hs:205).  A debugging aid, not tuned: plain device recursion below a Bih.
+__device__ int debug_count_node(const DScene& S, int ni, const Ray& r, Flt d) {
+    GlomeNode nd = S.nodes[ni];
+    while (nd.type == GLOME_TEX || nd.type == GLOME_TAG || nd.type == GLOME_NOSHADOW) { ni = nd.a; nd = S.nodes[ni]; }
+    switch (nd.type) {
+        case GLOME_GROUP: {
+            int c = 0;
+            for (int i = 0; i < nd.b; i++) c += debug_count_node(S, nd.a + i, r, d);
+            return c;
+        }
+        case GLOME_INSTANCE: {
+            const Flt* xfm = S.dpool + nd.b;
+            Vec newdir = invxfm_vec(xfm, r.d);
+            Vec neworig = invxfm_point(xfm, r.o);
+            Flt lenscale = vlen(newdir);
+            Flt invlenscale = 1 / lenscale;
+            return debug_count_node(S, nd.a, mkray(neworig, vscale(newdir, invlenscale)), d * lenscale);
+        }
+        case GLOME_BOUND:
+            if (inside_node(S, nd.a, r.o) || shadow_node<-1>(S, nd.a, r, d, 0, nullptr)) return debug_count_node(S, nd.b, r, d) + 1;
+            return 0;
+        case GLOME_INNERBOUND: return debug_count_node(S, nd.b, r, d);
+        case GLOME_BIH: {
+            Bbox bb = ldbb(S.dpool + nd.b);
+            Flt near_, far_;
+            bbclip_ub(r, bb, near_, far_);  // no clip by d at the root (Bih.hs:381)
+            const Flt drx = 1 / r.d.x, dry = 1 / r.d.y, drz = 1 / r.d.z;
+            const bool linear = (nd.c & GLOME_BIH_LINEAR_SPHERES) != 0;
+            TravEnt stack[64];
+            int sp = 0, c = 0, ref = nd.a;
+            for (;;) {
+                bool pop = false;
+                if (ref < 0) {
+                    if (!linear) {  // a bare sphere counts 0
+                        int lf, lc;
+                        glome_bih_leaf(ref, S.ipool, &lf, &lc);
+                        for (int i = 0; i < lc; i++) c += debug_count_node(S, lf + i, r, fmin_(d, far_));
+                    }
+                    pop = true;
+                } else {
+                    c++;
+                    if (near_ > far_) pop = true;  // (RayMiss,0) wrapped with 1: only possible at the root
+                    else {
+                        const GlomeBihNode n = S.bih[ref];
+                        Flt dr_ = (n.axis == 0) ? drx : ((n.axis == 1) ? dry : drz);
+                        Flt o = (n.axis == 0) ? r.o.x : ((n.axis == 1) ? r.o.y : r.o.z);
+                        Flt dl = (n.lsplit - o) * dr_;
+                        Flt dr = (n.rsplit - o) * dr_;
+                        const bool fwd = dr_ > 0;
+                        const Flt dn = fwd ? dl : dr, df = fwd ? dr : dl;
+                        const int c1 = fwd ? n.left : n.right, c2 = fwd ? n.right : n.left;
+                        const bool v1 = near_ < dn, v2 = df < far_;
+                        if (v1 && v2 && sp < 64) { stack[sp].ref = c2; stack[sp].near_ = fmax_(df, near_); stack[sp].far_ = far_; sp++; }
+                        if (v1) { ref = c1; far_ = fmin_(dn, far_); }
+                        else if (v2) { ref = c2; near_ = fmax_(df, near_); }
+                        else pop = true;
+                    }
+                }
+                if (pop) {
+                    if (sp == 0) break;
+                    sp--;
+                    ref = stack[sp].ref; near_ = stack[sp].near_; far_ = stack[sp].far_;
+                }
+            }
+            return c;
+        }
+        default: return 0;
+    }
+}
+
 struct DCamera { Vec pos, fwd, up, right; };
 __device__ __forceinline__ void getCoordsf(int width, int height, Flt xf, Flt yf, Flt& xc, Flt& yc) {  // Glome.hs:119-140
     Flt widthf = (Flt)width, heightf = (Flt)height;

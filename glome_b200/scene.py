@@ -439,6 +439,14 @@ class Scene:
                                            _ptr(depth), _ptr(hits) if want_hits else None))
         return (rgba, depth, hits) if want_hits else (rgba, depth)
 
+    def debug_count(self, rays, tmax=1000000.0):
+        """rayint_debug's box count per ray (Bih.hs:378-412)."""
+        rays = _f64(rays, (-1, 6))
+        t, stride = self._tmax(tmax, len(rays))
+        out = np.zeros(len(rays), dtype=np.int32)
+        L.check(self.lib.glome_debug_count_batch(self.h, len(rays), _ptr(rays), _ptr(t), stride, _ptr(out)))
+        return out
+
     def get_tags(self, cam, width, height, px, py, recurs=3):
         """getTags' (Glome.hs:410-414): (tag ids of the object under the pixel, partial flag, primary hit record)."""
         tags = (C.c_int32 * L.GLOME_MAX_STACK)()

@@ -219,7 +219,8 @@ typedef struct GlomeRenderOpts {
     int32_t tile_first;    /* multi-GPU sharding: render tiles i with i % tile_stride == tile_first */
     int32_t tile_stride;   /* 1 = all tiles                                                  */
     int32_t want_rgb8;     /* also pack 0x00RRGGBB (rgbf, Glome.hs:107-110)                  */
-    int32_t reserved;
+    int32_t debug_heatmap; /* 1: get_color_debug (Glome.hs:57-60): r += (n mod 30)/60, g += n/1000 with n = rayint_debug's
+                              count for the camera ray; GLOME_MODE_ONE_RAY only */
 } GlomeRenderOpts;
 
 typedef struct GlomeRenderStats {
@@ -263,6 +264,11 @@ int glome_inside_batch(GlomeScene* s, int64_t n, const double* pts, uint8_t* ins
  * rgba = n*4 doubles (ColorA, not premultiplied), depth = n doubles (ridepth of the primary hit). */
 int glome_trace_batch(GlomeScene* s, int64_t n, const double* rays, const double* tmax,
                       int tmax_stride, int recurs, double* rgba, double* depth, GlomeHit* hits_or_null);
+/* rayint_debug's Int for each ray (Solid.hs:155, Bih.hs:378-412, Bound.hs:37-42): the number of BIH boxes the
+ * reference's own walk enters -- the input of GlomeView's heat map (get_color_debug, Glome.hs:57-60; render it
+ * with GlomeRenderOpts.debug_heatmap). */
+int glome_debug_count_batch(GlomeScene* s, int64_t n, const double* rays, const double* tmax, int tmax_stride,
+                            int32_t* counts);
 /* getTags' / get_tags (Glome.hs:69-72, 410-414): the tags of the object under pixel (px, py), what GlomeView prints
  * on a click.  tags receives min(*ntags, max_tags) ids, head (innermost) first.  *partial = 1 when the hit's textures
  * can yield Reflect / Refract / Warp materials: the reference then prepends the tags gathered by those recursive

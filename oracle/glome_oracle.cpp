@@ -1328,8 +1328,71 @@ static void tile_list(int width, int height, int blocksize, std::vector<int>& re
             rects.push_back(xs[i].second); rects.push_back(ys[j].second);
         }
 }
+// ---- rayint_debug: the Int half of (Rayint, Int) -----------------------------------------------------
+// The count does not depend on what is hit: Bih adds 1 per branch entered on the unculled walk and passes
+// `fmin d far` to its leaves (Bih.hs:378-412); [s] sums (Solid.hs:312,329); Instance transforms the ray and scales
+// d (Solid.hs:447-461); Bound adds 1 when its gate passes (Bound.hs:37-42); InnerBound defers to sb (Bound.hs:107);
+// Tag / Tex / NoShadow pass through, OnlyShadow is (RayMiss,0) (Tex.hs:55,67,79,90); everything else is the class
+// default ((rayint ...), 0) (Solid.hs:205).
+static int64_t debug_count(const Scene& S, int ni, const Ray& r, Flt d);
+static int64_t debug_count_bih(const Scene& S, const Ray& r, Flt d, const Flt* dirr, const Flt* o, int ref, Flt near_, Flt far_) {
+    if (ref < 0) {
+        int32_t lf, lc;
+        glome_bih_leaf(ref, S.ipool.data(), &lf, &lc);
+        int64_t c = 0;
+        for (int i = 0; i < lc; i++) c += debug_count(S, lf + i, r, fmin_(d, far_));
+        return c;
+    }
+    const GlomeBihNode& n = S.bih[ref];
+    Flt dr_ = dirr[n.axis], oo = o[n.axis];
+    Flt dl = (n.lsplit - oo) * dr_;
+    Flt dr = (n.rsplit - oo) * dr_;
+    int64_t c = 1;
+    if (near_ > far_) return c;
+    if (dr_ > 0) {
+        if (near_ < dl) c += debug_count_bih(S, r, d, dirr, o, n.left, near_, fmin_(dl, far_));
+        if (dr < far_) c += debug_count_bih(S, r, d, dirr, o, n.right, fmax_(dr, near_), far_);
+    } else {
+        if (near_ < dr) c += debug_count_bih(S, r, d, dirr, o, n.right, near_, fmin_(dr, far_));
+        if (dl < far_) c += debug_count_bih(S, r, d, dirr, o, n.left, fmax_(dl, near_), far_);
+    }
+    return c;
+}
+static int64_t debug_count(const Scene& S, int ni, const Ray& r, Flt d) {
+    const GlomeNode& nd = S.nodes[ni];
+    switch (nd.type) {
+        case GLOME_GROUP: {
+            int64_t c = 0;
+            for (int i = 0; i < nd.b; i++) c += debug_count(S, nd.a + i, r, d);
+            return c;
+        }
+        case GLOME_INSTANCE: {
+            const Flt* xfm = &S.dpool[nd.b];
+            Vec newdir = invxfm_vec(xfm, r.d);
+            Vec neworig = invxfm_point(xfm, r.o);
+            Flt lenscale = vlen(newdir);
+            Flt invlenscale = 1 / lenscale;
+            Ray ir = {neworig, vscale(newdir, invlenscale)};
+            return debug_count(S, nd.a, ir, d * lenscale);
+        }
+        case GLOME_BIH: {
+            Bbox bb = ldbb(S, nd.b);
+            Flt near_, far_;
+            bbclip_ub(r, bb, near_, far_);  // Interval near far = bbclip r bb: no clip by d at the root (Bih.hs:381)
+            Flt dirr[3] = {1 / r.d.x, 1 / r.d.y, 1 / r.d.z}, o[3] = {r.o.x, r.o.y, r.o.z};
+            return debug_count_bih(S, r, d, dirr, o, nd.a, near_, far_);
+        }
+        case GLOME_TEX: case GLOME_TAG: case GLOME_NOSHADOW: return debug_count(S, nd.a, r, d);
+        case GLOME_BOUND:
+            if (inside(S, nd.a, r.o) || shadow(S, nd.a, r, d, 0)) return debug_count(S, nd.b, r, d) + 1;
+            return 0;
+        case GLOME_INNERBOUND: return debug_count(S, nd.b, r, d);
+        default: return 0;
+    }
+}
+
 static void renderTile(const Scene& S, const Camera& cam, int width, int height, const int* rect, int recurs, int tint,
-                       TColor* img) {
+                       TColor* img, int heatmap = 0) {
     // Glome.hs:162-176
     int xtmin = rect[0], ytmin = rect[1], tw = rect[2], th = rect[3];
     for (int i = 0; i < tw * th; i++) {
@@ -1337,6 +1400,13 @@ static void renderTile(const Scene& S, const Camera& cam, int width, int height,
         Flt xc, yc;
         getCoordsf(width, height, (Flt)x, (Flt)y, xc, yc);
         TColor c = get_color(S, cam, xc, yc, recurs);
+        if (heatmap) {  // get_color_debug (Glome.hs:57-60)
+            Vec dir = vnorm(vadd3(cam.fwd, vscale(cam.right, -xc), vscale(cam.up, yc)));
+            Ray dray = {cam.pos, dir};
+            int64_t dbg = debug_count(S, S.root, dray, infinity_);
+            c.r = ((Flt)(dbg % 30) / 60) + c.r;
+            c.g = c.g + ((Flt)dbg / 1000);
+        }
         if (tint) c.r = c.r + (c.d / 400);
         img[(size_t)y * width + x] = c;
     }
@@ -1642,6 +1712,10 @@ void orc_rayint_batch(void* h, int64_t n, const double* rays, const double* tmax
         fill_hit(ri, &out[i]);
     });
 }
+void orc_debug_count_batch(void* h, int64_t n, const double* rays, const double* tmax, int tmax_stride, int32_t* out, int threads) {
+    Scene& S = ((OrcScene*)h)->S;
+    parallel_for(n, threads, S, [&](int64_t i) { out[i] = (int32_t)debug_count(S, S.root, ldray(rays, i), tmax[tmax_stride ? i : 0]); });
+}
 void orc_shadow_batch(void* h, int64_t n, const double* rays, const double* tmax, int tmax_stride, uint8_t* occ,
                       int threads) {
     Scene& S = ((OrcScene*)h)->S;
@@ -1702,7 +1776,7 @@ void orc_render(void* h, const GlomeCamera* gc, int width, int height, const Glo
             if (k >= (int)sel.size()) break;
             const int* rect = &rects[4 * sel[k]];
             if (o->mode == GLOME_MODE_ADAPTIVE_AA) renderTileSubsample(S, cam, width, height, rect, o->recurs, o->thresholds, img);
-            else renderTile(S, cam, width, height, rect, o->recurs, o->tint_depth, img);
+            else renderTile(S, cam, width, height, rect, o->recurs, o->tint_depth, img, o->debug_heatmap);
             if (rgb8)
                 for (int y = rect[1]; y < rect[1] + rect[3]; y++)
                     for (int x = rect[0]; x < rect[0] + rect[2]; x++) {

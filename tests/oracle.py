@@ -36,6 +36,7 @@ def load():
     lib.orc_scene_destroy.argtypes = [_vp]
     lib.orc_rayint_batch.argtypes = [_vp, C.c_int64, _vp, _vp, C.c_int, _vp, C.c_int]
     lib.orc_shadow_batch.argtypes = [_vp, C.c_int64, _vp, _vp, C.c_int, _vp, C.c_int]
+    lib.orc_debug_count_batch.argtypes = [_vp, C.c_int64, _vp, _vp, C.c_int, _vp, C.c_int]
     lib.orc_inside_batch.argtypes = [_vp, C.c_int64, _vp, _vp, C.c_int]
     lib.orc_trace_batch.argtypes = [_vp, C.c_int64, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_int]
     lib.orc_tile_count.argtypes = [C.c_int, C.c_int, C.c_int]
@@ -136,6 +137,13 @@ class OracleScene:
         if want_tags:
             res.append(tags)
         return tuple(res)
+
+    def debug_count(self, rays, tmax=1000000.0, threads=NCPU):
+        rays = _f64(rays, (-1, 6))
+        t, stride = self._tmax(tmax, len(rays))
+        out = np.zeros(len(rays), dtype=np.int32)
+        self.lib.orc_debug_count_batch(self.h, len(rays), _ptr(rays), _ptr(t), stride, _ptr(out), threads)
+        return out
 
     def render(self, cam, width, height, opts, want_rgb8=False, threads=NCPU, max_tiles=0, out=None):
         tc = out if out is not None else np.zeros((height, width, 5))

@@ -33,3 +33,30 @@ def test_get_tags_matches_the_oracle_on_testscene():
             assert tags == ref
         n_tagged += bool(tags)
     assert n_tagged > 20 and n_partial > 0  # the scene has tagged objects and mirror / warp surfaces
+
+
+@pytest.mark.parametrize("config,n", [(2, 30000), (1, 0), (3, 20000)])
+def test_rayint_debug_count_and_heat_map(config, n):
+    """rayint_debug's box count (Bih.hs:378-412 and the instances that forward or sum it) per camera ray, and the
+    frame get_color_debug makes of it (Glome.hs:57-60), against the oracle's restatement."""
+    b = G.SceneBuilder()
+    root, cam, rec = b.config_scene(config, n)
+    fs = b.flatten(root)
+    gs, osc = G.Scene(fs, 0), O.OracleScene(fs)
+    w, h = 96, 64
+    ys, xs = np.mgrid[0:h, 0:w]
+    rays = G.camera_rays(cam, w, h, xs.ravel(), ys.ravel())
+    g, o = gs.debug_count(rays), osc.debug_count(rays)
+    assert np.array_equal(g, o)
+    assert g.max() > 0
+    short = osc.debug_count(rays, 30.0)
+    assert np.array_equal(gs.debug_count(rays, 30.0), short)
+    opts = G.render_opts(mode=L.MODE_ONE_RAY, recurs=rec, debug_heatmap=1)
+    tg, _, _ = gs.render(cam, w, h, opts)
+    to, _ = osc.render(cam, w, h, opts)
+    assert np.abs(tg[..., :4] - to[..., :4]).max() <= 1e-6
+    plain, _, _ = gs.render(cam, w, h, G.render_opts(mode=L.MODE_ONE_RAY, recurs=rec))
+    cnt = g.reshape(h, w)
+    assert np.array_equal(tg[..., 1], plain[..., 1] + cnt / 1000.0)
+    with pytest.raises(L.GlomeError):  # the heat map is per-pixel get_color_debug: not defined for the AA pipeline
+        gs.render(cam, w, h, G.render_opts(mode=L.MODE_ADAPTIVE_AA, recurs=rec, debug_heatmap=1))
