@@ -195,6 +195,24 @@ __global__ void __launch_bounds__(128) k_inside_batch(DScene S, long long n, con
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         out[i] = inside_node(S, S.root, vec(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2])) ? 1 : 0;
 }
+// the pick query's variant: also the TraceResult's tag list, n*(2+16) int32 = {count, overflow, tags...}
+template <bool GEN>
+__global__ void __launch_bounds__(128) k_trace_tags(DScene S, long long n, const double* __restrict__ rays,
+                                                    const double* __restrict__ tmax, int stride, int recurs,
+                                                    GlomeHit* __restrict__ hits, int* __restrict__ tags) {
+    RayCounters rc = {0, 0, 0, {0, 0, 0, 0}};
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        ColorA c;
+        Hit h;
+        TagList tl;
+        tl_clear(tl);
+        trace<GEN, TagList*>(S, 0, S.root, ld_ray(rays, i), tmax[stride ? i : 0], recurs, c, h, rc, &tl);
+        if (hits) hit_out(h, hits + i);
+        int* o = tags + (2 + GDEV_TAGLIST_CAP) * i;
+        o[0] = tl.n; o[1] = tl.overflow;
+        for (int k = 0; k < GDEV_TAGLIST_CAP; k++) o[2 + k] = k < tl.n ? tl.v[k] : -1;
+    }
+}
 template <bool GEN>
 __global__ void __launch_bounds__(128) k_trace_batch(DScene S, long long n, const double* __restrict__ rays,
                                                      const double* __restrict__ tmax, int stride, int recurs,
@@ -431,7 +449,6 @@ struct GlomeScene {
     int tev_used;
     bool time_traversal;
     int n_scene_lights;
-    std::vector<char> tex_nonsurface;  // texture id -> may yield a material other than Surface (tags gathered by recursion)
 };
 
 extern "C" int glome_device_count(void) {
@@ -561,32 +578,6 @@ extern "C" int glome_scene_create(const GlomeFlatScene* desc, int device, GlomeS
     if ((rc = upload(s, desc->dpool, (size_t)desc->n_dpool, &s->d.dpool))) return rc;
     if ((rc = upload(s, desc->textures, (size_t)desc->n_textures, &s->d.textures))) return rc;
     if ((rc = upload(s, desc->materials, (size_t)desc->n_materials, &s->d.materials))) return rc;
-    {   // which textures can produce a non-Surface material (their traces gather tags, see glome_get_tags)
-        std::vector<char> mat_ns((size_t)desc->n_materials, 0);
-        for (int pass = 0; pass < 4; pass++)  // Blend / AdditiveLayers nest: a few sweeps reach the fixpoint of practical scenes
-            for (int i = 0; i < desc->n_materials; i++) {
-                const GlomeMaterial& m = desc->materials[i];
-                if (m.kind == GLOME_MAT_SURFACE) continue;
-                if (m.kind == GLOME_MAT_BLEND) {
-                    bool a = m.a < 0 || m.a >= desc->n_materials || mat_ns[m.a], b = m.b < 0 || m.b >= desc->n_materials || mat_ns[m.b];
-                    mat_ns[i] = (a || b) ? 1 : 0;
-                } else if (m.kind == GLOME_MAT_ADDITIVE) {
-                    char any = 0;
-                    for (int j = 0; j < m.b; j++) {
-                        int id = (m.a + j >= 0 && m.a + j < desc->n_ipool) ? desc->ipool[m.a + j] : -1;
-                        if (id < 0 || id >= desc->n_materials || mat_ns[id]) any = 1;
-                    }
-                    mat_ns[i] = any;
-                } else mat_ns[i] = 1;
-            }
-        s->tex_nonsurface.assign((size_t)desc->n_textures, 0);
-        for (int i = 0; i < desc->n_textures; i++) {
-            const GlomeTexture& t = desc->textures[i];
-            bool a = t.a < 0 || t.a >= desc->n_materials || mat_ns[t.a];
-            bool b = t.kind != GLOME_TEX_UNIFORM && (t.b < 0 || t.b >= desc->n_materials || mat_ns[t.b]);
-            s->tex_nonsurface[i] = (a || b) ? 1 : 0;
-        }
-    }
     if ((rc = upload(s, desc->lights, (size_t)desc->n_lights, &s->d.lights))) return rc;
     if ((rc = upload(s, ls.data(), ls.size(), &s->d.lightsets))) return rc;
     CK(cudaMalloc((void**)&s->queue_count, sizeof(int)));
@@ -773,12 +764,11 @@ extern "C" int glome_trace_batch(GlomeScene* s, int64_t n, const double* rays, c
 }
 
 // getTags' / get_tags (Glome.hs:69-72, 410-414): the tag list of whatever is under pixel (px, py) -- what
-// GlomeView prints on a mouse click.  One camera ray (getCoords, Glome.hs:119-128; get_rayint, :27-33) through the
-// same trace kernel as glome_trace_batch.  The reference returns `ts ++ tags`: the hit's own tag stack preceded
-// by the tags gathered by Reflect / Refract / Warp recursion; the device materialises the hit's own stack only
-// (the render path discards tags, Glome.hs:53-55), so for those materials the prefix is missing: *partial = 1.
+// GlomeView prints on a mouse click.  One camera ray (getCoords, Glome.hs:119-128; get_rayint, :27-33) through
+// trace instantiated with a tag list: `ts ++ tags`, the tags gathered by Reflect / Refract / Warp recursion
+// followed by the hit's own tag stack (Trace.hs:82).
 extern "C" int glome_get_tags(GlomeScene* s, const GlomeCamera* cam, int width, int height, int px, int py, int recurs,
-                              int32_t* tags, int max_tags, int* ntags, int* partial, GlomeHit* hit_out) {
+                              int32_t* tags, int max_tags, int* ntags, int* truncated, GlomeHit* hit_out) {
     if (!s || !cam || !tags || !ntags || width <= 0 || height <= 0 || max_tags < 0) { g_err = "bad argument"; return GLOME_EINVAL; }
     const Flt xf = (Flt)px, yf = (Flt)py, widthf = (Flt)width, heightf = (Flt)height;
     const Flt xc = (((xf / widthf) * 2) - 1) * (widthf / heightf);
@@ -787,20 +777,28 @@ extern "C" int glome_get_tags(GlomeScene* s, const GlomeCamera* cam, int width, 
     const Vec right = vec(cam->right[0], cam->right[1], cam->right[2]);
     const Vec dir = vnorm(vadd3(fwd, vscale(right, -xc), vscale(up, yc)));
     double ray[6] = {cam->pos[0], cam->pos[1], cam->pos[2], dir.x, dir.y, dir.z};
-    double tmax = GLM_INFINITY, rgba[4], depth;
+    double tmax = GLM_INFINITY;
+    CK(cudaSetDevice(s->device));
+    int rc;
+    if ((rc = grow(s, 0, 48))) return rc;
+    if ((rc = grow(s, 1, 8))) return rc;
+    if ((rc = grow(s, 2, (2 + GDEV_TAGLIST_CAP) * sizeof(int)))) return rc;
+    if ((rc = grow(s, 3, sizeof(GlomeHit)))) return rc;
+    CK(cudaMemcpy(s->bw[0], ray, 48, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->bw[1], &tmax, 8, cudaMemcpyHostToDevice));
+    if (s->scene_class == GLOME_CLASS_FLAT)
+        k_trace_tags<false><<<1, 128>>>(s->d, 1, (const double*)s->bw[0], (const double*)s->bw[1], 0, recurs, (GlomeHit*)s->bw[3], (int*)s->bw[2]);
+    else
+        k_trace_tags<true><<<1, 128>>>(s->d, 1, (const double*)s->bw[0], (const double*)s->bw[1], 0, recurs, (GlomeHit*)s->bw[3], (int*)s->bw[2]);
+    s->launches++;
+    CK(cudaGetLastError());
+    int out[2 + GDEV_TAGLIST_CAP];
     GlomeHit h;
-    int rc = glome_trace_batch(s, 1, ray, &tmax, 0, recurs, rgba, &depth, &h);
-    if (rc) return rc;
-    *ntags = h.hit ? h.ntag : 0;
-    for (int i = 0; i < *ntags && i < max_tags && i < GLOME_MAX_STACK; i++) tags[i] = h.tag[i];
-    if (partial) {
-        *partial = 0;
-        if (h.hit && recurs > 0)
-            for (int i = 0; i < h.ntex && i < GLOME_MAX_STACK; i++) {
-                int t = h.tex[i];
-                if (t < 0 || t >= (int)s->tex_nonsurface.size() || s->tex_nonsurface[t]) *partial = 1;
-            }
-    }
+    CK(cudaMemcpy(out, s->bw[2], sizeof(out), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&h, s->bw[3], sizeof(h), cudaMemcpyDeviceToHost));
+    *ntags = out[0];
+    for (int i = 0; i < out[0] && i < max_tags; i++) tags[i] = out[2 + i];
+    if (truncated) *truncated = (out[1] || out[0] > max_tags) ? 1 : 0;
     if (hit_out) *hit_out = h;
     return GLOME_OK;
 }

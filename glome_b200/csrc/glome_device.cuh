@@ -1265,9 +1265,26 @@ __device__ __forceinline__ void mat_load(const DScene& S, int id, MatVal& m) {
     for (int i = 0; i < 8; i++) m.p[i] = g->p[i];
 }
 
-template <bool GEN>
+// The [t] half of a TraceResult (Trace.hs:59-82; Shader.hs:116,154,171-183).  The render path discards it
+// (Glome.hs:53-55), so the kernels that render instantiate trace / mpostshade with NoTags (an empty type: no register,
+// no code); the pick query (getTags', Glome.hs:410-414) instantiates them with a TagList*.  Every function APPENDS
+// its list to what the caller passed.  Capacity 16, the tail is dropped and flagged.
+#define GDEV_TAGLIST_CAP 16
+struct TagList { int n; int overflow; int v[GDEV_TAGLIST_CAP]; };
+struct NoTags {};
+__device__ __forceinline__ void tl_clear(TagList& t) { t.n = 0; t.overflow = 0; }
+__device__ __forceinline__ void tl_push(TagList* t, int x) { if (t->n < GDEV_TAGLIST_CAP) t->v[t->n++] = x; else t->overflow = 1; }
+__device__ __forceinline__ void tl_append(TagList* dst, const TagList& src) {  // dst ++ src
+    for (int i = 0; i < src.n; i++) tl_push(dst, src.v[i]);
+    dst->overflow |= src.overflow;
+}
+__device__ __forceinline__ void tl_append(NoTags, const TagList&) {}
+template <typename TL> struct tl_on { static const bool value = true; };
+template <> struct tl_on<NoTags> { static const bool value = false; };
+
+template <bool GEN, typename TL = NoTags>
 __device__ void trace(const DScene& S, int lightset, int sld, const Ray& ray, Flt depth, int recurs, ColorA& outc, Hit& ri,
-                      RayCounters& rc);
+                      RayCounters& rc, TL tl = TL());
 
 template <bool GEN>
 __device__ __forceinline__ void mpreshade(const DScene& S, int lightset, int scene, const Hit& ri, LightCtx& ctx,
@@ -1325,9 +1342,9 @@ __device__ __forceinline__ void shade_surface(const LightCtx& lights, const Flt*
     outc = mkca(ar + dr, ag + dg, ab + db, alpha);
 }
 
-template <bool GEN>
+template <bool GEN, typename TL = NoTags>
 __device__ void mpostshade(const DScene& S, int ls, LightCtx& lights, const MatVal& mat, const Ray& ray, int s, const Hit& ri,
-                           int recurs, ColorA& outc, RayCounters& rc) {
+                           int recurs, ColorA& outc, RayCounters& rc, TL tl = TL()) {
     // Shader.hs:82-184 (ri is a RayHit here)
     const Vec dir = ray.d;
     const Vec n = ri.norm;
@@ -1343,9 +1360,9 @@ __device__ void mpostshade(const DScene& S, int ls, LightCtx& lights, const MatV
             if constexpr (GEN) {
                 MatVal m;
                 mat_load(S, mat.a, m);
-                mpostshade<true>(S, ls, lights, m, ray, s, ri, recurs, ca, rc);
+                mpostshade<true, TL>(S, ls, lights, m, ray, s, ri, recurs, ca, rc, tl);  // tagsa ++ tagsb (Shader.hs:184)
                 mat_load(S, mat.b, m);
-                mpostshade<true>(S, ls, lights, m, ray, s, ri, recurs, cb, rc);
+                mpostshade<true, TL>(S, ls, lights, m, ray, s, ri, recurs, cb, rc, tl);
             } else {
                 // flat-class scenes only hold Surface materials: no recursion needed
                 if (!lights.done) mpreshade<false>(S, ls, s, ri, lights, rc);
@@ -1365,7 +1382,7 @@ __device__ void mpostshade(const DScene& S, int ls, LightCtx& lights, const MatV
                     ColorA c;
                     Hit h;
                     rc.secondary++;
-                    trace<true>(S, ls, s, mkray(vscaleadd(p, outdir, GLM_DELTA), outdir), GLM_INFINITY, recurs - 1, c, h, rc);
+                    trace<true, TL>(S, ls, s, mkray(vscaleadd(p, outdir, GLM_DELTA), outdir), GLM_INFINITY, recurs - 1, c, h, rc, tl);  // refltags
                     outc = mkca(c.r, c.g, c.b, c.a * refl);
                 } else outc = mkca(0, 0, 0, 1);
                 return;
@@ -1377,7 +1394,7 @@ __device__ void mpostshade(const DScene& S, int ls, LightCtx& lights, const MatV
                     ColorA a;
                     Hit h;
                     rc.secondary++;
-                    trace<true>(S, ls, s, mkray(vscaleadd(p, outdir, GLM_DELTA), outdir), GLM_INFINITY, recurs - 1, a, h, rc);
+                    trace<true, TL>(S, ls, s, mkray(vscaleadd(p, outdir, GLM_DELTA), outdir), GLM_INFINITY, recurs - 1, a, h, rc, tl);  // refltags ++
                     Flt eta = (vdot(n, eyedir) > 0) ? ior : 1 / ior;
                     Flt c1 = vdot(dir, n);
                     Flt cs2 = 1 - (eta * eta) * (1 - (c1 * c1));
@@ -1386,7 +1403,7 @@ __device__ void mpostshade(const DScene& S, int ls, LightCtx& lights, const MatV
                     else {
                         Vec t = vadd(vscale(dir, eta), vscale(n, eta * c1 - sqrt(cs2)));
                         rc.secondary++;
-                        trace<true>(S, ls, s, mkray(vscaleadd(p, t, GLM_DELTA), t), GLM_INFINITY, recurs - 1, b, h, rc);
+                        trace<true, TL>(S, ls, s, mkray(vscaleadd(p, t, GLM_DELTA), t), GLM_INFINITY, recurs - 1, b, h, rc, tl);  // refrtags (Shader.hs:154)
                     }
                     outc = mkca(a.r * refl + b.r * refr, a.g * refl + b.g * refr, a.b * refl + b.b * refr, a.a * refl + b.a * refr);
                 } else outc = mkca(0, 0, 0, 0);
@@ -1396,9 +1413,17 @@ __device__ void mpostshade(const DScene& S, int ls, LightCtx& lights, const MatV
                 ColorA fc, wc;
                 Hit fh, wh;
                 rc.secondary += 2;
-                trace<true>(S, ls, mat.a, ri.ray, GLM_INFINITY, recurs - 1, fc, fh, rc);
                 Ray wr = xfm_ray(S.dpool + mat.d, mkray(ri.pos, vnorm(ray.d)));  // TestScene.hs:169-173
-                trace<true>(S, mat.c, mat.b, wr, ridepth(fh), recurs - 1, wc, wh, rc);
+                if constexpr (tl_on<TL>::value) {  // (fcolor, ftags) or (wcolor, wtags) (Shader.hs:171-175)
+                    TagList ft, wt;
+                    tl_clear(ft); tl_clear(wt);
+                    trace<true, TagList*>(S, ls, mat.a, ri.ray, GLM_INFINITY, recurs - 1, fc, fh, rc, &ft);
+                    trace<true, TagList*>(S, mat.c, mat.b, wr, ridepth(fh), recurs - 1, wc, wh, rc, &wt);
+                    tl_append(tl, (ridepth(fh) < ridepth(wh)) ? ft : wt);
+                } else {
+                    trace<true>(S, ls, mat.a, ri.ray, GLM_INFINITY, recurs - 1, fc, fh, rc);
+                    trace<true>(S, mat.c, mat.b, wr, ridepth(fh), recurs - 1, wc, wh, rc);
+                }
                 if (ridepth(fh) < ridepth(wh)) outc = fc;
                 else outc = wc;
                 return;
@@ -1409,7 +1434,7 @@ __device__ void mpostshade(const DScene& S, int ls, LightCtx& lights, const MatV
                     ColorA c;
                     MatVal m;
                     mat_load(S, S.ipool[mat.a + i], m);
-                    mpostshade<true>(S, ls, lights, m, ray, s, ri, recurs, c, rc);
+                    mpostshade<true, TL>(S, ls, lights, m, ray, s, ri, recurs, c, rc, tl);  // concat taglists (Shader.hs:179)
                     r = r + c.r * c.a; g = g + c.g * c.a; b = b + c.b * c.a;
                     prod = prod * (1 - aclamp(c.a));
                 }
@@ -1436,11 +1461,11 @@ __device__ __forceinline__ void eval_texture(const DScene& S, int tex, const Hit
     m.p[0] = scale;
 }
 
-// trace (Trace.hs:59-82).  Tag lists produced by the shader are not materialised on the device;
-// ri carries the primary hit's own tag stack.
-template <bool GEN>
+// trace (Trace.hs:59-82).  ri carries the primary hit's own tag stack; with a TagList* the TraceResult's tag list
+// `ts ++ tags` is appended to *tl, where ts = tagsb_k ++ ... ++ tagsb_1 over the hit's textures (Trace.hs:68-79).
+template <bool GEN, typename TL>
 __device__ void trace(const DScene& S, int lightset, int sld, const Ray& ray, Flt depth, int recurs, ColorA& outc, Hit& ri,
-                      RayCounters& rc) {
+                      RayCounters& rc, TL tl) {
     outc = mkca(0, 0, 0, 0);
     if (recurs == 0) { hit_clear(ri); return; }
     rayint_scene<GEN>(S, sld, ray, depth, ri, &rc.cnt);
@@ -1449,13 +1474,25 @@ __device__ void trace(const DScene& S, int lightset, int sld, const Ray& ray, Fl
     ctxb.done = 0;
     ctxb.n = 0;
     ColorA colora = mkca(0, 0, 0, 0);
+    TagList ts;
+    if constexpr (tl_on<TL>::value) tl_clear(ts);
     for (int i = 0; i < ri.tex.n; i++) {
         if (colora.a + GLM_DELTA >= 1) continue;  // opaque (Trace.hs:50)
         MatVal m;
         eval_texture(S, ri.tex.v[i], ri, m, rc);
         ColorA colorb;
-        mpostshade<GEN>(S, lightset, ctxb, m, ray, sld, ri, recurs, colorb, rc);
+        if constexpr (tl_on<TL>::value) {
+            TagList tb;
+            tl_clear(tb);
+            mpostshade<GEN, TagList*>(S, lightset, ctxb, m, ray, sld, ri, recurs, colorb, rc, &tb);
+            tl_append(&tb, ts);  // tagsb ++ tagsa
+            ts = tb;
+        } else mpostshade<GEN>(S, lightset, ctxb, m, ray, sld, ri, recurs, colorb, rc);
         colora = cafold(colora, colorb);
+    }
+    if constexpr (tl_on<TL>::value) {
+        tl_append(tl, ts);
+        for (int i = 0; i < ri.tag.n; i++) tl_push(tl, ri.tag.v[i]);  // ts ++ tags
     }
     outc = colora;
 }

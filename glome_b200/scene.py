@@ -448,13 +448,14 @@ class Scene:
         return out
 
     def get_tags(self, cam, width, height, px, py, recurs=3):
-        """getTags' (Glome.hs:410-414): (tag ids of the object under the pixel, partial flag, primary hit record)."""
-        tags = (C.c_int32 * L.GLOME_MAX_STACK)()
-        n, partial = C.c_int32(), C.c_int32()
+        """getTags' (Glome.hs:410-414): (tag ids of the trace result under the pixel, truncated flag, primary hit)."""
+        cap = 16
+        tags = (C.c_int32 * cap)()
+        n, trunc = C.c_int32(), C.c_int32()
         hit = L.GlomeHit()
-        L.check(self.lib.glome_get_tags(self.h, C.byref(cam), width, height, px, py, recurs, tags, L.GLOME_MAX_STACK,
-                                        C.byref(n), C.byref(partial), C.byref(hit)))
-        return list(tags[:min(n.value, L.GLOME_MAX_STACK)]), bool(partial.value), hit
+        L.check(self.lib.glome_get_tags(self.h, C.byref(cam), width, height, px, py, recurs, tags, cap,
+                                        C.byref(n), C.byref(trunc), C.byref(hit)))
+        return list(tags[:min(n.value, cap)]), bool(trunc.value), hit
 
     def render(self, cam, width, height, opts=None, want_rgb8=False, out=None, rgb8_out=None):
         """renderTiles: returns (tcolor[h,w,5], rgb8[h,w] or None, stats)."""

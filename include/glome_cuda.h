@@ -269,12 +269,12 @@ int glome_trace_batch(GlomeScene* s, int64_t n, const double* rays, const double
  * with GlomeRenderOpts.debug_heatmap). */
 int glome_debug_count_batch(GlomeScene* s, int64_t n, const double* rays, const double* tmax, int tmax_stride,
                             int32_t* counts);
-/* getTags' / get_tags (Glome.hs:69-72, 410-414): the tags of the object under pixel (px, py), what GlomeView prints
- * on a click.  tags receives min(*ntags, max_tags) ids, head (innermost) first.  *partial = 1 when the hit's textures
- * can yield Reflect / Refract / Warp materials: the reference then prepends the tags gathered by those recursive
- * traces, which the device does not materialise.  hit_out (optional) is the primary Rayint. */
+/* getTags' / get_tags (Glome.hs:69-72, 410-414): the tag list of the trace result under pixel (px, py), what
+ * GlomeView prints on a click: `ts ++ tags` (Trace.hs:82), i.e. the tags gathered by Reflect / Refract / Warp
+ * recursion followed by the hit's own tag stack, head first.  *ntags = list length (device capacity 16);
+ * tags receives min(*ntags, max_tags) ids; *truncated = 1 when the list was cut.  hit_out (optional) = the primary Rayint. */
 int glome_get_tags(GlomeScene* s, const GlomeCamera* cam, int width, int height, int px, int py, int recurs,
-                   int32_t* tags, int max_tags, int* ntags, int* partial, GlomeHit* hit_out);
+                   int32_t* tags, int max_tags, int* ntags, int* truncated, GlomeHit* hit_out);
 /* renderTiles (+ blitTile)  (Glome.hs:379-386, 353-358).  tcolor = w*h*5 doubles (r,g,b,a,depth),
  * row-major, or NULL when only the packed image is wanted; rgb8 = w*h uint32 or NULL.  Pixels of tiles not selected by tile_first/tile_stride are
  * left untouched. */
