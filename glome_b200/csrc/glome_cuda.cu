@@ -19,6 +19,9 @@
 #include "glome_device.cuh"
 #include "glome_wave.cuh"
 
+#ifndef GLOME_AA_SPEC_RATIO
+#define GLOME_AA_SPEC_RATIO 0.6  /* flat scenes: speculate AA passes 1-4 when the last frame traced this share of the pixel centres */
+#endif
 #ifndef GEN_THREADS
 #define GEN_THREADS 64
 #endif
@@ -389,6 +392,9 @@ __global__ void __launch_bounds__(256) k_aa_decide(DecideParams P) {
         }
         if (P.spec && P.pass < 5) {
             if (need) st_tc(P.v, (size_t)y * width + x, ld_tc(P.spec, (size_t)y * width + x));
+            // keep counting what the adaptive schedule would have traced (the next frame's schedule looks at it)
+            unsigned int mm = __ballot_sync(0xffffffffu, need);
+            if (mm && lane == __ffs(mm) - 1) atomicAdd(P.queue_count, __popc(mm));
             continue;
         }
         // warp-aggregated compaction
@@ -449,6 +455,12 @@ struct GlomeScene {
     int tev_used;
     bool time_traversal;
     int n_scene_lights;
+    // adaptive-AA schedule memory (flat scenes): how many pixel centres the last AA frame traced (or, when it
+    // speculated, would have traced) in passes 1-4, read back asynchronously into pinned memory
+    int* aa_counts_host;        // [0] unused, [1..4] per pass
+    cudaEvent_t aa_ev;
+    bool aa_valid;
+    int aa_w, aa_h, aa_first, aa_stride, aa_bs;
 };
 
 extern "C" int glome_device_count(void) {
@@ -601,6 +613,8 @@ extern "C" int glome_scene_create(const GlomeFlatScene* desc, int device, GlomeS
     s->w_counter_next = 0;
     s->tev_used = 0; s->time_traversal = false;
     s->n_scene_lights = ls[1];
+    s->aa_counts_host = nullptr; s->aa_valid = false; s->aa_ev = nullptr;
+    s->aa_w = s->aa_h = s->aa_first = s->aa_stride = s->aa_bs = 0;
     if (s->scene_class == GLOME_CLASS_FLAT && !getenv("GLOME_FLAT_MEGAKERNEL") && build_segments(desc, s->segs) &&
         ls[0] + ls[1] <= 32) {
         CK(cudaMalloc((void**)&s->segs_dev, sizeof(gwave::Seg) * s->segs.size()));
@@ -626,6 +640,8 @@ extern "C" int glome_scene_destroy(GlomeScene* s) {
     cudaFree(s->segs_dev); cudaFree(s->w_hit_t); cudaFree(s->w_hit_seg); cudaFree(s->w_hit_item); cudaFree(s->w_hit_sub);
     cudaFree(s->w_hit_flags); cudaFree(s->w_surf); cudaFree(s->w_occl); cudaFree(s->w_squeue); cudaFree(s->w_squeue_count);
     cudaFree(s->w_counters);
+    if (s->aa_counts_host) cudaFreeHost(s->aa_counts_host);
+    if (s->aa_ev) cudaEventDestroy(s->aa_ev);
     cudaEventDestroy(s->ev0); cudaEventDestroy(s->ev1);
     for (cudaEvent_t e : s->tev) cudaEventDestroy(e);
     delete s;
@@ -923,6 +939,11 @@ static int persistent_grid(GlomeScene* s, K kernel, int threads) {
     return s->sm_count * b;
 }
 
+static bool event_done(cudaEvent_t e) {
+    if (cudaEventQuery(e) == cudaSuccess) return true;
+    cudaGetLastError();  // cudaErrorNotReady is not an error here: do not leave it for the next CK()
+    return false;
+}
 static void trav_mark(GlomeScene* s, cudaStream_t st) {
     if (!s->time_traversal) return;
     if (s->tev_used >= (int)s->tev.size()) {
@@ -1035,7 +1056,8 @@ extern "C" int glome_render_dev(GlomeScene* s, const GlomeCamera* cam, int width
         W.g.nby = g.nby; W.g.slots_per_tile = g.slots_per_tile;
         W.cam = P.cam; W.recurs = o->recurs; W.tint = o->tint_depth;
         W.tile_first = o->tile_first; W.tile_stride = o->tile_stride; W.n_sel = n_sel;
-        size_t need = (o->mode == GLOME_MODE_ONE_RAY) ? (size_t)n_sel * g.slots_per_tile : npix;
+        size_t need = (size_t)n_sel * g.slots_per_tile;  // padded 8x4 micro-tiles of the selected tiles
+        if (o->mode != GLOME_MODE_ONE_RAY && npix > need) need = npix;
         if ((rc = wave_reserve(s, need))) return rc;
         s->w_counter_next = 0;
         CK(cudaMemsetAsync(s->w_counters, 0, sizeof(unsigned int) * 1024, st));
@@ -1073,7 +1095,30 @@ extern "C" int glome_render_dev(GlomeScene* s, const GlomeCamera* cam, int width
             // interpreter is latency-bound per warp), so passes 1-4 are speculated: every pixel centre is traced
             // once, up front, and the per-pass decisions copy from that buffer.  get_color is a pure function of the
             // sample position, so the frame is bit-identical to the adaptive schedule; only the ray count differs.
-            const bool speculate = !s->use_wave && !getenv("GLOME_NO_SPECULATE");
+            bool speculate = !s->use_wave && !getenv("GLOME_NO_SPECULATE");
+            if (s->use_wave) {
+                // Flat scenes: a wave is cheap per ray but five dependent waves are not (each sits on its latency
+                // floor), so the same speculation pays when the adaptive schedule ends up tracing most pixel centres
+                // anyway (a cloud of small spheres: 95 %) and costs rays when it does not (a smooth mesh: 30 %).
+                // The schedule of this frame follows what the previous frame of the same geometry did; the frame
+                // itself is bit-identical either way.
+                const char* e = getenv("GLOME_AA_SPECULATE");
+                if (e) speculate = atoi(e) != 0;
+                else if (s->aa_valid && s->aa_w == width && s->aa_h == height && s->aa_first == o->tile_first &&
+                         s->aa_stride == o->tile_stride && s->aa_bs == o->blocksize && event_done(s->aa_ev)) {
+                    long long centres = 0, traced = 0;
+                    for (int k = 0; k < n_sel; k++) {
+                        int ti = o->tile_first + k * o->tile_stride, tx = ti / g.nty, ty = ti % g.nty;
+                        centres += (long long)std::min(g.bs, width - tx * g.bs) * std::min(g.bs, height - ty * g.bs);
+                    }
+                    for (int p = 1; p <= 4; p++) traced += s->aa_counts_host[p];
+                    speculate = (double)traced >= GLOME_AA_SPEC_RATIO * (double)centres;
+                }
+                if (!s->aa_counts_host) {
+                    CK(cudaMallocHost((void**)&s->aa_counts_host, 8 * sizeof(int)));
+                    CK(cudaEventCreateWithFlags(&s->aa_ev, cudaEventDisableTiming));
+                }
+            }
             D.spec = nullptr;
             if (speculate) {
                 if (s->spec_pix < npix) {
@@ -1081,9 +1126,15 @@ extern "C" int glome_render_dev(GlomeScene* s, const GlomeCamera* cam, int width
                     CK(cudaMalloc((void**)&s->spec, npix * 5 * sizeof(double)));
                     s->spec_pix = npix;
                 }
-                TraceParams P0 = P;
-                P0.out = s->spec; P0.tint = 0;
-                if ((rc = launch_trace_c<0>(s, P0, st))) return rc;
+                if (s->use_wave) {
+                    W.mode = 0; W.out = s->spec; W.tint = 0;
+                    if ((rc = launch_wave(s, W, (long long)n_sel * g.slots_per_tile, st))) return rc;
+                    W.tint = o->tint_depth;
+                } else {
+                    TraceParams P0 = P;
+                    P0.out = s->spec; P0.tint = 0;
+                    if ((rc = launch_trace_c<0>(s, P0, st))) return rc;
+                }
                 D.spec = s->spec;
             }
             for (int pass = 1; pass <= 5; pass++) {
@@ -1093,6 +1144,7 @@ extern "C" int glome_render_dev(GlomeScene* s, const GlomeCamera* cam, int width
                 k_aa_decide<<<n_sel, 256, 0, st>>>(D);
                 s->launches++;
                 CK(cudaGetLastError());
+                if (s->use_wave && pass < 5) CK(cudaMemcpyAsync(s->aa_counts_host + pass, s->queue_count, sizeof(int), cudaMemcpyDeviceToHost, st));
                 if (speculate && pass < 5) continue;
                 if (s->use_wave) {
                     W.mode = pass < 5 ? 1 : 5; W.queue = s->queue; W.queue_count = s->queue_count; W.v = s->v;
@@ -1100,6 +1152,11 @@ extern "C" int glome_render_dev(GlomeScene* s, const GlomeCamera* cam, int width
                     if ((rc = launch_wave(s, W, (long long)npix, st))) return rc;
                 } else if (pass < 5) { P.out = s->v; if ((rc = launch_trace_c<1>(s, P, st))) return rc; }
                 else { P.out = tcolor_dev; if ((rc = launch_trace_c<5>(s, P, st))) return rc; }
+            }
+            if (s->use_wave) {
+                CK(cudaEventRecord(s->aa_ev, st));
+                s->aa_valid = true;
+                s->aa_w = width; s->aa_h = height; s->aa_first = o->tile_first; s->aa_stride = o->tile_stride; s->aa_bs = o->blocksize;
             }
         }
         if (rgb8_dev) {

@@ -147,3 +147,31 @@ def test_shadow_agrees_with_rayint_where_the_reference_says_so():
     for d in (1000000.0, 150.0, 40.0):
         hit = gs.rayint(rays, d)["hit"] != 0
         assert np.array_equal(gs.shadow(rays, d).astype(bool), hit)
+
+
+def test_aa_schedule_memory_keeps_the_frame_bit_identical():
+    """Flat scenes: when the previous AA frame traced most pixel centres, the next one traces them all in one wave and
+    lets the pass decisions copy.  The frame must not change; only the ray count does.  A smooth mesh
+    keeps the adaptive schedule."""
+    for config, n, w, h, expect_spec in ((2, 1000000, 720, 480, True), (3, 2000000, 3840, 2160, False)):
+        b = G.SceneBuilder()
+        root, cam, rec = b.config_scene(config, n)
+        fs = b.flatten(root)
+        gs = G.Scene(fs)
+        opts = G.render_opts(mode=L.MODE_ADAPTIVE_AA, recurs=rec)
+        f1, _, s1 = gs.render(cam, w, h, opts)
+        f2, _, s2 = gs.render(cam, w, h, opts)
+        f3, _, s3 = gs.render(cam, w, h, opts)
+        assert f1.tobytes() == f2.tobytes() == f3.tobytes()
+        if expect_spec:
+            assert s2.launches < s1.launches and s2.rays_primary >= s1.rays_primary and s3.launches == s2.launches
+        else:
+            assert s2.launches == s1.launches and s2.rays_primary == s1.rays_primary
+        if config == 2:  # and both schedules equal the oracle on a sample of tiles
+            osc = O.OracleScene(fs)
+            rects = O.tile_rects(w, h, 65)
+            o2 = G.render_opts(mode=L.MODE_ADAPTIVE_AA, recurs=rec, tile_first=0, tile_stride=max(1, len(rects) // 6))
+            to = np.full((h, w, 5), np.nan)
+            osc.render(cam, w, h, o2, out=to)
+            sel = ~np.isnan(to[..., 0])
+            assert np.array_equal(f2[sel], to[sel])
