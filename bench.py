@@ -299,7 +299,7 @@ def main():
         if world == 1:
             scene.render_ptr(cam, WIDTH, HEIGHT, opts_e2e, None, pinned.data_ptr(), dev=False)
         else:
-            rdr.render_frame_host()
+            rdr.render_frame_host(copy_on=0)
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) * 1e3
         if i >= args.warmup:
@@ -340,7 +340,7 @@ def main():
                     "d2h_bytes_per_step": WIDTH * HEIGHT * 4, "ms_per_step": e2e_ms_per_step,
                     "fps": 1000.0 / e2e_ms_per_step,
                     "api": "glome_render (C-ABI, host buffers): camera+options in, 0x00RRGGBB frame to pinned host memory"
-                           if world == 1 else "ShardedRenderer.render_frame_host: render + NCCL all-gather + D2H on every rank"},
+                           if world == 1 else "ShardedRenderer.render_frame_host: render + NCCL all-gather on every rank + D2H of the frame on rank 0 (the displaying rank)"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",

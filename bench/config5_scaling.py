@@ -60,7 +60,7 @@ for i in range(WARM + STEPS):
     flush.fill_(1)
     barrier()
     t0 = time.perf_counter()
-    rdr.render_frame_host()
+    rdr.render_frame_host(copy_on=0)
     torch.cuda.synchronize()
     if i >= WARM:
         e2e.append((time.perf_counter() - t0) * 1e3)

@@ -100,9 +100,12 @@ class ShardedRenderer:
         self.launches += launches
         return launches
 
-    def render_frame_host(self):
-        """End-to-end frame: render + gather + device->host copy of the packed image into pinned memory."""
+    def render_frame_host(self, copy_on=None):
+        """End-to-end frame: render + gather + device->host copy of the packed image into pinned memory.
+        copy_on=None: every rank ends with the frame in host memory; copy_on=k: only rank k does (the rank that
+        displays it, as GlomeView's single blit loop does), the others just wait for their part of the gather."""
         n = self.render_frame_dev()
-        self.host_rgb8.copy_(self.rgb8, non_blocking=True)
+        if copy_on is None or copy_on == self.rank:
+            self.host_rgb8.copy_(self.rgb8, non_blocking=True)
         self.torch.cuda.current_stream(self.dev).synchronize()
         return self.host_rgb8, n
