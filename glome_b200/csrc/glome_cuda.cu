@@ -345,28 +345,42 @@ __global__ void __launch_bounds__(256) k_aa_decide(DecideParams P) {
     int xt, yt, tw, th;
     tile_rect(P.g, ti, xt, yt, tw, th);
     const int width = P.g.width;
-    const int npix = tw * th;
     const int lane = threadIdx.x & 31;
-    for (int base = 0; base < npix; base += blockDim.x) {
+    // Only the pass's own pixels are enumerated (1/8, 1/8, 1/4, 1/2 and all of the tile): rows x slots-per-row, a slot
+    // past the tile's edge is skipped.  The reference's initial fill of the tile buffer (MUV.replicate, Glome.hs:231) is
+    // never read -- every pixel a pass looks at belongs to an earlier pass (Appendix C) and out-of-tile reads are
+    // answered by getc -- so it is not written.
+    int rows, per_row;
+    switch (P.pass) {
+        case 1: case 2: rows = (th + 1) >> 1; per_row = (((tw + 1) >> 1) + 1) >> 1; break;  // dy even; every other even dx
+        case 3: rows = th >> 1; per_row = tw >> 1; break;                                      // dx, dy odd
+        case 4: rows = th; per_row = (tw + 1) >> 1; break;                                     // dx + dy odd
+        default: rows = th; per_row = tw; break;
+    }
+    const int nslots = rows * per_row;
+    for (int base = 0; base < nslots; base += blockDim.x) {
         int i = base + threadIdx.x;
         bool need = false;
         int x = 0, y = 0;
-        if (i < npix) {
-            int dx = i % tw, dy = i / tw;
+        bool member = false;
+        int dx = 0, dy = 0;
+        if (i < nslots) {
+            const int ry = i / per_row, k = i % per_row;
+            switch (P.pass) {
+                case 1: dy = 2 * ry; dx = 2 * (2 * k + (ry & 1)); break;          // (dx + dy) mod 4 == 0  (Glome.hs:241-250)
+                case 2: dy = 2 * ry; dx = 2 * (2 * k + ((ry + 1) & 1)); break;    // (dx + dy) mod 4 == 2  (:251-262)
+                case 3: dy = 2 * ry + 1; dx = 2 * k + 1; break;                    // (:272-281)
+                case 4: dy = ry; dx = 2 * k + ((ry + 1) & 1); break;               // (:283-295)
+                default: dy = ry; dx = k; break;                                   // (:301-319)
+            }
+            member = dx < tw && dy < th;
+        }
+        if (member) {
             x = xt + dx; y = yt + dy;
             size_t pix = (size_t)y * width + x;
-            bool member;
-            switch (P.pass) {
-                case 1: member = ((dx | dy) & 1) == 0 && ((dx + dy) & 3) == 0; break;   // Glome.hs:241-250
-                case 2: member = ((dx | dy) & 1) == 0 && ((dx + dy) & 3) == 2; break;   // :251-262
-                case 3: member = (dx & 1) && (dy & 1); break;                           // :272-281
-                case 4: member = ((dx + dy) & 1) == 1; break;                           // :283-295
-                default: member = true; break;                                          // :301-319
-            }
             if (P.pass == 1) {
-                st_tc(P.v, pix, tc_init());  // MUV.replicate (0,0,0,0,infinity) (:231)
-                need = member;
-            } else if (member) {
+                need = true;
+            } else {
                 TC a, b, c, d;
                 if (P.pass == 2) {
                     a = getc(P.v, width, xt, yt, tw, th, x - 2, y); b = getc(P.v, width, xt, yt, tw, th, x, y + 2);
