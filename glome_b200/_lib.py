@@ -109,6 +109,9 @@ SIGNATURES = {
     "glome_render_dev": (C.c_int, [_vp, _P(GlomeCamera), C.c_int, C.c_int, _P(GlomeRenderOpts), _vp, _vp,
                                    _P(GlomeRenderStats), _vp]),
     "glome_scene_launches": (C.c_int64, [_vp]),
+    "glome_multi_create": (C.c_int, [_P(GlomeFlatScene), C.c_int, _ip, _P(_vp)]),
+    "glome_multi_destroy": (C.c_int, [_vp]),
+    "glome_multi_render": (C.c_int, [_vp, _P(GlomeCamera), C.c_int, C.c_int, _P(GlomeRenderOpts), _vp, _vp, _P(GlomeRenderStats)]),
     "glome_debug_count_batch": (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_int, _vp]),
     "glome_get_tags": (C.c_int, [_vp, _P(GlomeCamera), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, C.c_int, _ip, _ip,
                                  _P(GlomeHit)]),

@@ -1303,3 +1303,168 @@ extern "C" int glome_tiles_unpack_all_dev(int width, int height, int blocksize, 
     CK(cudaGetLastError());
     return GLOME_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// One process driving several GPUs: what a Haskell caller links, with no torch and no
+// NCCL in the picture.  The scene is replicated; device k renders tiles i with i % N == k on its own stream; each
+// device packs its tiles and copies them to the first device with cudaMemcpyPeerAsync (NVLink P2P); the first device
+// unpacks all of them into the frame.  Same kernels, same tile order, so the frame equals the 1-GPU frame bit for bit.
+// ---------------------------------------------------------------------------------------------
+struct GlomeMulti {
+    int n;
+    std::vector<int> dev;
+    std::vector<GlomeScene*> scene;
+    std::vector<cudaStream_t> stream;
+    std::vector<cudaEvent_t> done;
+    std::vector<double*> tc;         // per device: full TColor frame (its own tiles are valid)
+    std::vector<uint32_t*> rgb;      // per device: packed image
+    std::vector<void*> pk;           // per device: its packed slots (largest element size)
+    void* gather;                    // device 0: N blocks of slots
+    size_t pix, pk_bytes, gather_bytes;
+    cudaEvent_t e0, e1;
+};
+
+static void multi_free_frames(GlomeMulti* m) {
+    for (int k = 0; k < m->n; k++) {
+        cudaSetDevice(m->dev[k]);
+        cudaFree(m->tc[k]); cudaFree(m->rgb[k]); cudaFree(m->pk[k]);
+        m->tc[k] = nullptr; m->rgb[k] = nullptr; m->pk[k] = nullptr;
+    }
+    cudaSetDevice(m->dev[0]);
+    cudaFree(m->gather);
+    m->gather = nullptr;
+    m->pix = 0; m->pk_bytes = 0; m->gather_bytes = 0;
+}
+
+extern "C" int glome_multi_destroy(GlomeMulti* m) {
+    if (!m) return GLOME_OK;
+    multi_free_frames(m);
+    for (int k = 0; k < m->n; k++) {
+        cudaSetDevice(m->dev[k]);
+        if (m->stream[k]) cudaStreamDestroy(m->stream[k]);
+        if (m->done[k]) cudaEventDestroy(m->done[k]);
+        if (m->scene[k]) glome_scene_destroy(m->scene[k]);
+    }
+    cudaSetDevice(m->dev[0]);
+    if (m->e0) cudaEventDestroy(m->e0);
+    if (m->e1) cudaEventDestroy(m->e1);
+    delete m;
+    return GLOME_OK;
+}
+
+extern "C" int glome_multi_create(const GlomeFlatScene* desc, int ndev, const int* devices, GlomeMulti** out) {
+    if (!desc || !out || ndev < 1 || ndev > 64 || !devices) { g_err = "bad argument"; return GLOME_EINVAL; }
+    GlomeMulti* m = new GlomeMulti();
+    m->n = ndev;
+    m->dev.assign(devices, devices + ndev);
+    m->scene.assign(ndev, nullptr); m->stream.assign(ndev, nullptr); m->done.assign(ndev, nullptr);
+    m->tc.assign(ndev, nullptr); m->rgb.assign(ndev, nullptr); m->pk.assign(ndev, nullptr);
+    m->gather = nullptr; m->pix = 0; m->pk_bytes = 0; m->gather_bytes = 0; m->e0 = nullptr; m->e1 = nullptr;
+    for (int k = 0; k < ndev; k++) {
+        int rc = glome_scene_create(desc, devices[k], &m->scene[k]);
+        if (rc) { glome_multi_destroy(m); return rc; }
+        if (cudaSetDevice(devices[k]) != cudaSuccess || cudaStreamCreateWithFlags(&m->stream[k], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&m->done[k], cudaEventDisableTiming) != cudaSuccess) {
+            g_err = "glome_multi_create: stream / event creation failed"; glome_multi_destroy(m); return GLOME_ECUDA;
+        }
+        if (k > 0) {  // peer access both ways with the gathering device (already-enabled is fine)
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, devices[k], devices[0]);
+            if (can) { cudaDeviceEnablePeerAccess(devices[0], 0); cudaGetLastError(); }
+            cudaSetDevice(devices[0]);
+            cudaDeviceCanAccessPeer(&can, devices[0], devices[k]);
+            if (can) { cudaDeviceEnablePeerAccess(devices[k], 0); cudaGetLastError(); }
+        }
+    }
+    cudaSetDevice(devices[0]);
+    if (cudaEventCreate(&m->e0) != cudaSuccess || cudaEventCreate(&m->e1) != cudaSuccess) {
+        g_err = "glome_multi_create: event creation failed"; glome_multi_destroy(m); return GLOME_ECUDA;
+    }
+    *out = m;
+    return GLOME_OK;
+}
+
+// renderTiles over the GPUs of this process.  tcolor (w*h*5 doubles) and / or rgb8 (w*h uint32) are host buffers.
+// stats: ray counts summed over the devices, kernel_ms = device time of the whole frame on the gathering device's
+// clock (render on all devices + peer copies + unpack).
+extern "C" int glome_multi_render(GlomeMulti* m, const GlomeCamera* cam, int width, int height, const GlomeRenderOpts* o,
+                                  double* tcolor, uint32_t* rgb8, GlomeRenderStats* stats) {
+    if (!m || !cam || !o || (!tcolor && !rgb8) || width <= 0 || height <= 0 || o->blocksize <= 0) { g_err = "bad argument"; return GLOME_EINVAL; }
+    if (o->tile_stride != 1 || o->tile_first != 0) { g_err = "glome_multi_render shards the tiles itself: tile_first = 0, tile_stride = 1"; return GLOME_EINVAL; }
+    const int N = m->n;
+    const size_t npix = (size_t)width * height;
+    const int slots = glome_tile_slots(width, height, o->blocksize, N);
+    const size_t slot_elems = (size_t)slots * o->blocksize * o->blocksize;
+    const size_t pk_bytes = slot_elems * 40;
+    if (m->pix < npix || m->pk_bytes < pk_bytes) {
+        multi_free_frames(m);
+        for (int k = 0; k < N; k++) {
+            CK(cudaSetDevice(m->dev[k]));
+            CK(cudaMalloc((void**)&m->tc[k], npix * 5 * sizeof(double)));
+            CK(cudaMalloc((void**)&m->rgb[k], npix * sizeof(uint32_t)));
+            CK(cudaMalloc(&m->pk[k], pk_bytes));
+        }
+        CK(cudaSetDevice(m->dev[0]));
+        CK(cudaMalloc(&m->gather, pk_bytes * N));
+        m->pix = npix; m->pk_bytes = pk_bytes; m->gather_bytes = pk_bytes * N;
+    }
+    CK(cudaSetDevice(m->dev[0]));
+    CK(cudaEventRecord(m->e0, m->stream[0]));
+    // the other devices start after e0 so that kernel_ms covers them
+    int rc;
+    for (int k = 0; k < N; k++) {
+        CK(cudaSetDevice(m->dev[k]));
+        if (k > 0) CK(cudaStreamWaitEvent(m->stream[k], m->e0, 0));
+        GlomeRenderOpts ok = *o;
+        ok.tile_first = k; ok.tile_stride = N;
+        if ((rc = glome_render_dev(m->scene[k], cam, width, height, &ok, m->tc[k], rgb8 ? m->rgb[k] : nullptr, nullptr, m->stream[k]))) return rc;
+    }
+    // gather: TColor first (if wanted), then the packed image, through the same buffers
+    for (int what = 0; what < 2; what++) {
+        const bool want = what == 0 ? (tcolor != nullptr) : (rgb8 != nullptr);
+        if (!want) continue;
+        const int eb = what == 0 ? 40 : 4;
+        const size_t bytes = slot_elems * eb;
+        for (int k = 1; k < N; k++) {
+            CK(cudaSetDevice(m->dev[k]));
+            const void* frame = what == 0 ? (const void*)m->tc[k] : (const void*)m->rgb[k];
+            if ((rc = glome_tiles_pack_dev(width, height, o->blocksize, k, N, eb, frame, m->pk[k], m->stream[k]))) return rc;
+            CK(cudaMemcpyPeerAsync((char*)m->gather + (size_t)k * bytes, m->dev[0], m->pk[k], m->dev[k], bytes, m->stream[k]));
+            CK(cudaEventRecord(m->done[k], m->stream[k]));
+        }
+        CK(cudaSetDevice(m->dev[0]));
+        for (int k = 1; k < N; k++) CK(cudaStreamWaitEvent(m->stream[0], m->done[k], 0));
+        void* frame0 = what == 0 ? (void*)m->tc[0] : (void*)m->rgb[0];
+        if (N > 1 && (rc = glome_tiles_unpack_all_dev(width, height, o->blocksize, N, 0, eb, m->gather, frame0, m->stream[0]))) return rc;
+        if (what == 0 && rgb8 && N > 1) {
+            // the gather buffer is reused for the packed image: the other devices may overwrite it only after this unpack
+            CK(cudaEventRecord(m->done[0], m->stream[0]));
+            for (int k = 1; k < N; k++) { CK(cudaSetDevice(m->dev[k])); CK(cudaStreamWaitEvent(m->stream[k], m->done[0], 0)); }
+            CK(cudaSetDevice(m->dev[0]));
+        }
+    }
+    CK(cudaEventRecord(m->e1, m->stream[0]));
+    if (tcolor) CK(cudaMemcpyAsync(tcolor, m->tc[0], npix * 5 * sizeof(double), cudaMemcpyDeviceToHost, m->stream[0]));
+    if (rgb8) CK(cudaMemcpyAsync(rgb8, m->rgb[0], npix * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->stream[0]));
+    CK(cudaStreamSynchronize(m->stream[0]));
+    if (stats) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, m->e0, m->e1);
+        GlomeRenderStats tot;
+        memset(&tot, 0, sizeof(tot));
+        for (int k = 0; k < N; k++) {
+            CK(cudaSetDevice(m->dev[k]));
+            CK(cudaStreamSynchronize(m->stream[k]));
+            GlomeRenderStats sk;
+            memset(&sk, 0, sizeof(sk));
+            read_stats(m->scene[k], &sk, 0, 0);
+            tot.rays_primary += sk.rays_primary; tot.rays_shadow += sk.rays_shadow; tot.rays_secondary += sk.rays_secondary;
+            tot.overflow_rays += sk.overflow_rays; tot.perlin_range += sk.perlin_range;
+            tot.visits_bih += sk.visits_bih; tot.tests_prim += sk.tests_prim; tot.visits_bvh += sk.visits_bvh; tot.tests_tri += sk.tests_tri;
+        }
+        tot.kernel_ms = ms;
+        *stats = tot;
+    }
+    return GLOME_OK;
+}
+

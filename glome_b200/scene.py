@@ -481,6 +481,39 @@ class Scene:
         return st
 
 
+class MultiScene:
+    """A FlatScene replicated on several GPUs of this process (glome_multi_*): tile i is rendered by device i % N and
+    the tiles are gathered on the first device by peer copies.  No torch, no NCCL: the C-ABI a Haskell caller uses."""
+
+    def __init__(self, flat, devices):
+        self.lib = L.load()
+        self.flat = flat
+        devs = (C.c_int32 * len(devices))(*devices)
+        h = C.c_void_p()
+        L.check(self.lib.glome_multi_create(C.byref(flat), len(devices), devs, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.lib.glome_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def render(self, cam, width, height, opts=None, want_rgb8=False, want_tcolor=True):
+        opts = opts or render_opts()
+        tc = np.zeros((height, width, 5)) if want_tcolor else None
+        rgb = np.zeros((height, width), dtype=np.uint32) if want_rgb8 else None
+        st = L.GlomeRenderStats()
+        L.check(self.lib.glome_multi_render(self.h, C.byref(cam), width, height, C.byref(opts),
+                                            _ptr(tc) if want_tcolor else None, _ptr(rgb) if want_rgb8 else None, C.byref(st)))
+        return tc, rgb, st
+
+
 def camera_rays(cam, width, height, xs, ys):
     """get_rayint's ray for pixel coordinates (Glome.hs:27-33, 119-128); numpy, for tests."""
     xs = np.asarray(xs, dtype=np.float64)

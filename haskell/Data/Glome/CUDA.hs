@@ -34,6 +34,7 @@ import Data.Glome.Scene (Camera(..))
 -- C side (include/glome_cuda.h)
 -- ---------------------------------------------------------------------------------------------
 data GlomeSceneH     -- opaque GlomeScene
+data GlomeMultiH
 data GlomeBuilderH   -- opaque GlomeBuilder
 data GlomeFlatSceneC -- struct GlomeFlatScene (filled by glome_sb_flatten)
 
@@ -51,6 +52,10 @@ foreign import ccall unsafe "glome_render_opts_default" c_opts_default :: Ptr Re
 foreign import ccall safe   "glome_get_tags"       c_get_tags       :: Ptr GlomeSceneH -> Ptr CDouble -> CInt -> CInt -> CInt -> CInt -> CInt -> Ptr Int32 -> CInt -> Ptr CInt -> Ptr CInt -> Ptr CudaHit -> IO CInt
 -- scene set-up on the GPU: the trees of `bih` / `mesh` (Bih.hs:211-285, Mesh.hs:69-113), same arrays as the host builders
 foreign import ccall safe   "glome_builder_set_build_device" c_builder_set_build_device :: Ptr GlomeBuilderH -> CInt -> IO CInt
+-- several GPUs driven by this process: tile i on device (i mod n), gathered on the first device by peer copies
+foreign import ccall safe   "glome_multi_create"   c_multi_create   :: Ptr GlomeFlatSceneC -> CInt -> Ptr CInt -> Ptr (Ptr GlomeMultiH) -> IO CInt
+foreign import ccall safe   "glome_multi_destroy"  c_multi_destroy  :: Ptr GlomeMultiH -> IO CInt
+foreign import ccall safe   "glome_multi_render"   c_multi_render   :: Ptr GlomeMultiH -> Ptr CDouble -> CInt -> CInt -> Ptr RenderOptsC -> Ptr CDouble -> Ptr Word32 -> Ptr () -> IO CInt
 -- NFF / SPD scene text (Spd.hs)
 foreign import ccall safe   "glome_sb_load_nff"    c_sb_load_nff    :: Ptr GlomeBuilderH -> CString -> Int64 -> Ptr CDouble -> Ptr CDouble -> Ptr Int64 -> IO CInt
 

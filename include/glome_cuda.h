@@ -308,6 +308,16 @@ int glome_tiles_unpack_dev(int width, int height, int blocksize, int tile_first,
 int glome_tiles_unpack_all_dev(int width, int height, int blocksize, int tile_stride, int skip_rank, int elem_bytes,
                                const void* gathered_dev, void* frame_dev, void* stream);
 
+/* One process driving several GPUs (what a Haskell program links: no torch, no NCCL).  The scene is replicated on
+ * devices[0..ndev); glome_multi_render renders tile i on device i % ndev (same kernels as glome_render), gathers the
+ * tiles on devices[0] with peer copies over NVLink and returns the frame in the caller's host buffers (either may be
+ * NULL).  The frame equals the 1-GPU frame bit for bit.  opts->tile_first / tile_stride must be 0 / 1. */
+typedef struct GlomeMulti GlomeMulti;
+int glome_multi_create(const GlomeFlatScene* desc, int ndev, const int* devices, GlomeMulti** out);
+int glome_multi_destroy(GlomeMulti* m);
+int glome_multi_render(GlomeMulti* m, const GlomeCamera* cam, int width, int height, const GlomeRenderOpts* opts,
+                       double* tcolor, uint32_t* rgb8, GlomeRenderStats* stats);
+
 /* Tile list helpers (chunk, Glome.hs:371-377): number of tiles and tile i's rect, in the order
  * renderTiles enumerates them (x-major). */
 int glome_tile_count(int width, int height, int blocksize);

@@ -65,3 +65,32 @@ def test_two_gpu_sharded_frame_is_bit_identical():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert ok
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("config,n,w,h", [(2, 30000, 333, 201), (1, 0, 160, 110)])
+def test_single_process_multi_gpu_frame_is_bit_identical(config, n, w, h):
+    """glome_multi_*: one process, tile i on device i % N, tiles gathered on the first device by peer copies.
+    Uses the box's GPUs when there are several; two handles on GPU 0 exercise the same code on a 1-GPU box."""
+    import glome_b200 as G
+    from glome_b200 import _lib as L
+    ndev = L.load().glome_device_count()
+    devices = list(range(min(ndev, 4))) if ndev >= 2 else [0, 0, 0]
+    b = G.SceneBuilder()
+    root, cam, rec = b.config_scene(config, n)
+    fs = b.flatten(root)
+    one = G.Scene(fs, 0)
+    multi = G.MultiScene(fs, devices)
+    for mode in (L.MODE_ONE_RAY, L.MODE_ADAPTIVE_AA):
+        opts = G.render_opts(mode=mode, recurs=rec)
+        t1, r1, s1 = one.render(cam, w, h, opts, want_rgb8=True)
+        for _ in range(2):  # the second frame may take the speculative AA schedule
+            tm, rm, sm = multi.render(cam, w, h, opts, want_rgb8=True)
+            assert tm.tobytes() == t1.tobytes()
+            assert rm.tobytes() == r1.tobytes()
+        tm2, _, _ = multi.render(cam, w, h, opts, want_rgb8=False)
+        assert tm2.tobytes() == t1.tobytes()
+        _, rm2, _ = multi.render(cam, w, h, opts, want_rgb8=True, want_tcolor=False)
+        assert rm2.tobytes() == r1.tobytes()
+    assert sm.rays_primary >= s1.rays_primary and sm.kernel_ms > 0
+    multi.close()
