@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "glome_device.cuh"
@@ -1412,12 +1413,28 @@ extern "C" int glome_multi_render(GlomeMulti* m, const GlomeCamera* cam, int wid
     CK(cudaEventRecord(m->e0, m->stream[0]));
     // the other devices start after e0 so that kernel_ms covers them
     int rc;
-    for (int k = 0; k < N; k++) {
-        CK(cudaSetDevice(m->dev[k]));
-        if (k > 0) CK(cudaStreamWaitEvent(m->stream[k], m->e0, 0));
-        GlomeRenderOpts ok = *o;
-        ok.tile_first = k; ok.tile_stride = N;
-        if ((rc = glome_render_dev(m->scene[k], cam, width, height, &ok, m->tc[k], rgb8 ? m->rgb[k] : nullptr, nullptr, m->stream[k]))) return rc;
+    {   // issue every device's frame from its own host thread: a frame is ~10 launches, and issuing eight of them one
+        // after the other from one thread would delay the last device by as much as it then computes
+        std::vector<int> rcs(N, 0);
+        std::vector<std::string> errs(N);
+        auto issue = [&](int k) {
+            auto body = [&]() -> int {
+                CK(cudaSetDevice(m->dev[k]));
+                if (k > 0) CK(cudaStreamWaitEvent(m->stream[k], m->e0, 0));
+                GlomeRenderOpts ok = *o;
+                ok.tile_first = k; ok.tile_stride = N;
+                return glome_render_dev(m->scene[k], cam, width, height, &ok, m->tc[k], rgb8 ? m->rgb[k] : nullptr, nullptr, m->stream[k]);
+            };
+            rcs[k] = body();
+            if (rcs[k]) errs[k] = g_err;  // g_err is thread-local: hand the message to the calling thread
+        };
+        std::vector<std::thread> th;
+        for (int k = 1; k < N; k++) th.emplace_back(issue, k);
+        issue(0);
+        for (auto& t : th) t.join();
+        for (int k = 0; k < N; k++)
+            if (rcs[k]) { g_err = errs[k]; return rcs[k]; }
+        CK(cudaSetDevice(m->dev[0]));
     }
     // gather: TColor first (if wanted), then the packed image, through the same buffers
     for (int what = 0; what < 2; what++) {
