@@ -1,36 +1,56 @@
 #!/usr/bin/env python
-"""bench.py -- the headline measurement (BASELINE.json metric: Mrays/s and fps).
+"""bench.py -- the headline measurement (BASELINE.json metric: Mrays/s and fps at 720x480 and 4K).
 
-A "step" is one frame of BASELINE.json configs[1]: a `bih` over 1 000 000 random spheres, 1920x1080,
-one camera ray per pixel plus a shadow ray per light and hit (2 point lights), FP64, Surface material.
+Headline step = one frame of BASELINE.json configs[4]: the 2 000 000-triangle Mesh (shared vertex / normal
+arrays, per-triangle texture / tag ids, a bih of occluder spheres above it, 2 point lights) rendered at
+3840x2160 with GlomeView's adaptive anti-aliasing (1/8 subsample -> <= 2 rays/pixel, Glome.hs:226-323), FP64.
+It is the largest single-GPU configuration and the one north_star shards across GPUs.
 
-  value    whole-job Mrays/s (primary + shadow + secondary rays resolved / device time), inputs
-           (the flattened scene) resident in HBM, framebuffer left in HBM
+  value    whole-job Mrays/s (primary + shadow + secondary rays resolved / device time), the flattened scene
+           resident in HBM, framebuffer left in HBM, L2 flushed between timed frames
   e2e      the same metric through the reference-facing C-ABI call `glome_render` with HOST buffers:
-           camera/options in, packed 0x00RRGGBB frame copied back to pinned host memory every step
-  roofline the persistent trace kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
-  cpu_baseline / --impl reference: the C++ oracle (a literal restatement of GlomeTrace; the Haskell
-           reference cannot be built here: no GHC) on the host cores, bounded sample of the same frame
+           camera / options in, packed 0x00RRGGBB frame copied back to pinned host memory every step
+  roofline the dominant kernel of the frame against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  configs  at N = 1: the same figures (ms, fps, Mrays/s, e2e, roofline, cpu_baseline) for all five
+           BASELINE.json configs, configs[0] (TestScene 720x480) included
+  cpu_baseline / --impl reference: the C++ oracle (a literal restatement of GlomeTrace; the Haskell reference
+           cannot be built here: no GHC) on the host cores, bounded sample of the same frame's tiles
 
 N > 1: the frame is sharded by 65x65 tile (tile i -> rank i mod N), scene replicated per GPU, one NCCL
-all-gather per frame: fixed total work, "scaling": "strong".
+all-gather per frame: fixed total work, "scaling": "strong".  `frame_hash` is the SHA-1 of the gathered
+0x00RRGGBB frame: it must be the same at N = 1, 2, 4, 8 (tiles never read across their edges).
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CONFIG = 2
-N_SPHERES = 1000000
-WIDTH, HEIGHT = 1920, 1080
-SEED = 2
+HEADLINE = 5
+# id -> BASELINE.json config.  scene = glome_sb_config_scene's id, n = its size argument
+CFG = {
+    1: dict(key="configs[0]", scene=1, n=0, w=720, h=480, aa=False,
+            what="GlomeView TestScene.geom'' (TestScene.hs:183-197; oak PRNG: random-1.2 SplitMix StdGen), 720x480, "
+                 "1 ray/pixel, maxdepth 3, 2 lights"),
+    2: dict(key="configs[1]", scene=2, n=1000000, w=1920, h=1080, aa=False,
+            what="bih of 1000000 random spheres, 1920x1080, 1 ray/pixel + shadow rays to 2 point lights"),
+    3: dict(key="configs[2]", scene=3, n=2000000, w=1920, h=1080, aa=False,
+            what="2000000-triangle Mesh (shared vertex/normal arrays, per-triangle tex/tag) + bih of 4096 occluder "
+                 "spheres, 1920x1080, 1 ray/pixel + shadow rays to 2 point lights"),
+    4: dict(key="configs[3]", scene=4, n=16, w=1280, h=720, aa=False,
+            what="CSG grid: 256 x difference(intersection[box, sphere, cylinder], cone)[, sphere] under a bih, mirrors, "
+                 "1280x720, 1 ray/pixel, recurs 5 (primary + 4 reflected generations)"),
+    5: dict(key="configs[4]", scene=5, n=2000000, w=3840, h=2160, aa=True,
+            what="2000000-triangle Mesh scene of configs[2] at 3840x2160, adaptive AA (1/8 subsample -> <= 2 rays/pixel, "
+                 "65x65 tiles = 2040 tiles), tile-sharded across the GPUs"),
+}
+SEEDS = {1: 42, 2: 2, 3: 3, 4: 4, 5: 3}
 
 
 def measured_peaks():
@@ -95,83 +115,283 @@ class ClockSampler:
         return out
 
 
-def build_scene(G, build_device=-1):
-    """build_device >= 0: the scene's `bih` is built on that GPU (glome_build.cu), -1: on the host; same tree."""
+def build_scene(G, cfg, build_device=-1):
+    """build_device >= 0: `bih` / `mesh` trees are built on that GPU (glome_build.cu), -1: on the host; same tree."""
+    c = CFG[cfg]
     b = G.SceneBuilder()
     b.set_build_device(build_device)
-    root, cam, recurs = b.config_scene(CONFIG, N_SPHERES, SEED)
+    root, cam, recurs = b.config_scene(c["scene"], c["n"], SEEDS[cfg])
     fs = b.flatten(root)
     return b, fs, cam, recurs
 
 
-def cpu_sample(G, fs, cam, recurs, seconds_target, threads):
-    """Time the oracle (CPU restatement) on a bounded sample of the frame: the first k tiles."""
+def mode_of(L, cfg):
+    return L.MODE_ADAPTIVE_AA if CFG[cfg]["aa"] else L.MODE_ONE_RAY
+
+
+def workload_config(cfg, n):
+    c = CFG[cfg]
+    return {"workload": "%s: %s" % (c["key"], c["what"]),
+            "mode": "adaptive_aa" if c["aa"] else "one_ray_per_pixel", "width": c["w"], "height": c["h"],
+            "blocksize": 65, "seed": SEEDS[cfg], "parallelism": "tiles%d" % n,
+            "l2": "flushed between timed steps (512 MiB write)"}
+
+
+def cpu_sample(G, cfg, fs, cam, recurs, seconds_target, threads):
+    """Time the oracle (CPU restatement) on a bounded sample of the frame's tiles (strided over the frame)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle as O  # the checker / CPU baseline: the only place bench.py touches oracle/
     from glome_b200 import _lib as L
     import numpy as np
+    c = CFG[cfg]
+    w, h = c["w"], c["h"]
     osc = O.OracleScene(fs)
-    opts = G.render_opts(mode=L.MODE_ONE_RAY, recurs=recurs)
-    frame = np.zeros((HEIGHT, WIDTH, 5))
-    ntiles = len(O.tile_rects(WIDTH, HEIGHT, 65))
-    # probe, then size the sample for ~seconds_target of wall time; tiles are taken with a stride so the
-    # sample covers the whole frame rather than one corner
+    frame = np.zeros((h, w, 5))
+    ntiles = len(O.tile_rects(w, h, 65))
+
     def run(k):
-        o = G.render_opts(mode=L.MODE_ONE_RAY, recurs=recurs, tile_first=0, tile_stride=max(1, ntiles // k))
+        o = G.render_opts(mode=mode_of(L, cfg), recurs=recurs, tile_first=0, tile_stride=max(1, ntiles // k))
         osc.stats()
         t0 = time.perf_counter()
-        osc.render(cam, WIDTH, HEIGHT, o, threads=threads, max_tiles=k, out=frame)
+        osc.render(cam, w, h, o, threads=threads, max_tiles=k, out=frame)
         dt = time.perf_counter() - t0
         st = osc.stats()
         rays = st["rays_primary"] + st["rays_shadow"] + st["rays_secondary"]
         return rays, dt, st
-    k = max(threads, 8)
-    rays, dt, st = run(min(k, ntiles))
+    k = min(ntiles, max(threads, 8))
+    rays, dt, st = run(k)
     if dt < seconds_target / 2 and k < ntiles:
         k = int(min(ntiles, max(k, k * seconds_target / max(dt, 1e-3))))
         rays, dt, st = run(k)
-    return {"rays": rays, "seconds": dt, "tiles": min(k, ntiles), "ntiles": ntiles, "stats": st, "osc": osc}
+    osc.close()
+    return {"rays": rays, "seconds": dt, "tiles": k, "ntiles": ntiles, "stats": st}
+
+
+def cpu_baseline_entry(r, threads):
+    return {"value": r["rays"] / r["seconds"] / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
+            "sample": "%d of %d 65x65 tiles (strided over the frame), %.1f s; C++ restatement of GlomeTrace (oracle/), "
+                      "not GHC: no Haskell toolchain in this image" % (r["tiles"], r["ntiles"], r["seconds"])}
 
 
 def reference_arm(args):
-    """--impl reference: the reference's CPU implementation of the path.  The reference is Haskell and
-    cannot be compiled here (no GHC in the image), so this is the C++ oracle, all host threads."""
+    """--impl reference: the reference's CPU implementation of the path on the headline config.  The reference is
+    Haskell and cannot be compiled here (no GHC in the image), so this is the C++ oracle on all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import glome_b200 as G
     threads = os.cpu_count() or 1
-    b, fs, cam, recurs = build_scene(G)
+    cfg = args.config
+    b, fs, cam, recurs = build_scene(G, cfg)
     per_step = max(2.0, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
     for _ in range(args.warmup):
-        cpu_sample(G, fs, cam, recurs, per_step / 4, threads)
-    rays = 0
-    secs = 0.0
-    tiles = 0
+        cpu_sample(G, cfg, fs, cam, recurs, per_step / 4, threads)
+    rays, secs, tiles, ntiles = 0, 0.0, 0, 0
     for _ in range(args.steps):
-        r = cpu_sample(G, fs, cam, recurs, per_step, threads)
+        r = cpu_sample(G, cfg, fs, cam, recurs, per_step, threads)
         rays += r["rays"]
         secs += r["seconds"]
-        tiles = r["tiles"]
-        ntiles = r["ntiles"]
+        tiles, ntiles = r["tiles"], r["ntiles"]
     v = rays / secs / 1e6
     line = {"impl": "reference", "metric": "Mrays/s", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * secs / max(1, args.steps),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(1),
+            "config": workload_config(cfg, 1),
             "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": threads, "kind": "port",
-                             "sample": "%d of %d 65x65 tiles per step (strided over the frame), one ray per pixel + "
-                                       "shadow rays; C++ restatement of GlomeTrace, not GHC" % (tiles, ntiles)},
+                             "sample": "%d of %d 65x65 tiles per step (strided over the frame); C++ restatement of "
+                                       "GlomeTrace, not GHC" % (tiles, ntiles)},
             "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
 
 
-def workload_config(n):
-    return {"workload": "configs[1]: bih of %d random spheres, %dx%d, 1 ray/pixel + shadow rays to 2 point lights"
-                        % (N_SPHERES, WIDTH, HEIGHT),
-            "mode": "one_ray_per_pixel", "recurs": 3, "blocksize": 65, "seed": SEED,
-            "parallelism": "tiles%d" % n, "l2": "flushed between timed steps (512 MiB write)"}
+class Ctx:
+    pass
+
+
+def measure(X, cfg, steps, warmup, with_cpu, cpu_seconds, setup_report=False):
+    """One config on this job's GPUs: device-resident frames (value), the dominant kernel (roofline), end to end
+    through the C-ABI with host buffers (e2e), optionally the CPU baseline.  Returns a dict on rank 0."""
+    G, L, torch, dist, np = X.G, X.L, X.torch, X.dist, X.np
+    from glome_b200.dist import ShardedRenderer
+    c = CFG[cfg]
+    w, h = c["w"], c["h"]
+    rank, world, local_rank = X.rank, X.world, X.local_rank
+    mode = mode_of(L, cfg)
+
+    setup = None
+    use_gpu_build = c["scene"] in (2, 3, 5)
+    if setup_report and rank == 0 and world == 1 and use_gpu_build:
+        hb = build_scene(G, cfg)[0]
+        host_ms = hb.last_build_ms()[3]
+        hb.close()
+        build_scene(G, cfg, local_rank)[0].close()  # untimed first build: module load, first cudaMalloc of the work space
+    b, fs, cam, recurs = build_scene(G, cfg, local_rank if use_gpu_build else -1)
+    if setup_report and rank == 0 and world == 1 and use_gpu_build:
+        gm = b.last_build_ms()
+        setup = {"last_tree_build_gpu_ms": {"h2d": gm[0], "device": gm[1], "d2h": gm[2], "wall": gm[3]},
+                 "last_tree_build_host_ms": host_ms, "host_threads": os.cpu_count(),
+                 "note": "the scene's last bih/mesh tree; same tree either way (tests/test_gpu_build.py); not part of the timed frame"}
+    scene = G.Scene(fs, local_rank)
+    rdr = ShardedRenderer(scene, cam, w, h, mode, recurs, rank=rank, world=world, want_tcolor=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        rdr.render_frame_dev()
+    barrier()
+    rdr.render_frame_dev(want_stats=True)
+    st = rdr.last_stats
+    counts = torch.tensor([st.rays_primary, st.rays_shadow, st.rays_secondary, st.overflow_rays], dtype=torch.float64,
+                          device="cuda")
+    if world > 1:
+        dist.all_reduce(counts)
+    cnt = counts.tolist()
+    rays_frame = cnt[0] + cnt[1] + cnt[2]
+    barrier()
+    # the gathered frame's hash: must not depend on N
+    frame_hash = hashlib.sha1(rdr.rgb8.cpu().numpy().tobytes()).hexdigest()[:16]
+
+    # ---- timed: device-resident (value) ----
+    rdr.launches = 0
+    evs = []
+    barrier()
+    t_wall0 = time.perf_counter()
+    for _ in range(steps):
+        X.flush.fill_(1)  # L2 flush, outside the event pair
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rdr.render_frame_dev()
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    tot = torch.tensor([sum(a.elapsed_time(bb) for a, bb in evs)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    ms_per_step = tot.item() / steps
+    launches = rdr.launches
+    value = rays_frame / (ms_per_step * 1e-3) / 1e6
+
+    # ---- the kernels of this rank's part of the frame, timed by CUDA events on the launching stream inside
+    # glome_render_dev (per kernel family) ----
+    opts1 = G.render_opts(mode=mode, recurs=recurs, tile_first=rank, tile_stride=world)
+    fam_ms = np.zeros(4)
+    fam_n = np.zeros(4)
+    kt = []
+    reps = min(steps, 8)
+    for _ in range(reps):
+        X.flush.fill_(1)
+        torch.cuda.synchronize()
+        s1 = scene.render_ptr(cam, w, h, opts1, rdr.tcolor.data_ptr(), 0, dev=True,
+                              stream=torch.cuda.current_stream().cuda_stream)
+        kt.append(s1.kernel_ms)
+        for k in range(4):
+            fam_ms[k] += s1.family_ms[k]
+            fam_n[k] = s1.family_launches[k]
+    fam_ms /= reps
+    kern_ms = float(np.mean(kt))
+
+    # ---- timed: end to end through the C-ABI with host buffers (e2e) ----
+    e2e_ms = []
+    pinned = torch.zeros((h, w), dtype=torch.int32).pin_memory()
+    opts_e2e = G.render_opts(mode=mode, recurs=recurs)
+    barrier()
+    n_e2e = max(3, min(steps, 10))
+    for i in range(3 + n_e2e):
+        X.flush.fill_(1)
+        barrier()
+        t0 = time.perf_counter()
+        if world == 1:
+            scene.render_ptr(cam, w, h, opts_e2e, None, pinned.data_ptr(), dev=False)
+        else:
+            rdr.render_frame_host(copy_on=0)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) * 1e3
+        if i >= 3:
+            e2e_ms.append(dt)
+    e2e_t = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_ms_per_step = e2e_t.item() / n_e2e
+    e2e_value = rays_frame / (e2e_ms_per_step * 1e-3) / 1e6
+
+    res = None
+    if rank == 0:
+        peaks, which = measured_peaks()
+        # algorithmic bytes of one frame's launches of the dominant kernel on this rank (DESIGN.md 3.5, SURVEY 8d): BIH
+        # branch 32 B, primitive record 32 B, BVH branch 128 B, triangle 32 B Tri + 72 B vertices, Instance 192 B,
+        # 24 B hit record out per ray
+        stl = s1
+        names = ["k_bih_traverse<closest>", "k_bih_traverse<any>", "k_bvh_closest", "k_gen_trace"]
+        bytes_f = [0.0] * 4
+        bih_total = stl.visits_bih * 32 + stl.tests_prim * 32
+        if fam_ms[3] > 0:  # general scenes: the one tracer does everything
+            bytes_f[3] = bih_total + stl.visits_instance * 192 + (stl.rays_primary + stl.rays_shadow + stl.rays_secondary) * 24
+        else:
+            # the two BIH traversal launches share their visit counters: split the bytes by their share of the time
+            tb = fam_ms[0] + fam_ms[1]
+            for k in (0, 1):
+                bytes_f[k] = (bih_total * (fam_ms[k] / tb) if tb > 0 else 0.0)
+            bytes_f[0] += stl.rays_primary * 24
+            bytes_f[1] += stl.rays_shadow * 4
+            bytes_f[2] = stl.visits_bvh * 128 + stl.tests_tri * 104 + stl.rays_primary * 24
+        # the dominant kernel: BIH closest + any are one kernel template (k_bih_traverse), reported together
+        groups = {"k_bih_traverse (persistent BIH traversal, closest-hit + any-hit launches)": (0, 1),
+                  "k_bvh_closest (persistent Mesh BVH traversal)": (2,),
+                  "k_gen_trace (persistent general-scene tracer: iterative scene-graph machine + shading)": (3,)}
+        gname, gidx = max(groups.items(), key=lambda kv: sum(fam_ms[i] for i in kv[1]))
+        g_ms = float(sum(fam_ms[i] for i in gidx))
+        g_bytes = float(sum(bytes_f[i] for i in gidx))
+        g_launch = int(sum(fam_n[i] for i in gidx))
+        achieved = g_bytes / (g_ms * 1e-3) / 1e9 if g_ms > 0 else 0.0
+        traffic, traffic_src = None, None
+        try:  # DRAM bytes of the same kernel from the committed ncu capture of this round (profiles/), N=1 only
+            if world == 1:
+                t = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+                e = t.get(c["key"])
+                if e:
+                    traffic = e["dram_bytes_per_frame"] / max(1, g_launch)
+                    traffic_src = "committed ncu --set full capture (%s), per launch; not measured in this run" % e["source"]
+        except Exception:
+            pass
+        res = {
+            "workload": "%s: %s" % (c["key"], c["what"]),
+            "ms_per_step": ms_per_step, "fps": 1000.0 / ms_per_step, "value": value, "unit": "Mrays/s",
+            "rays_per_frame": {"primary": cnt[0], "shadow": cnt[1], "secondary": cnt[2], "overflow": cnt[3]},
+            "frame_hash": frame_hash,
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 160,
+                    "d2h_bytes_per_step": w * h * 4, "ms_per_step": e2e_ms_per_step, "fps": 1000.0 / e2e_ms_per_step,
+                    "api": "glome_render (C-ABI, host buffers): camera+options in, 0x00RRGGBB frame to pinned host memory"
+                           if world == 1 else "ShardedRenderer.render_frame_host: render + NCCL all-gather on every rank + D2H of the frame on rank 0 (the displaying rank)"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": which, "kernel": gname, "launches_per_frame": g_launch,
+                         "kernel_ms_per_frame": g_ms, "avg_launch_ms": g_ms / max(1, g_launch),
+                         "share_of_step": g_ms / kern_ms if kern_ms > 0 else None, "frame_kernels_ms": kern_ms,
+                         "algorithmic_bytes_per_frame": g_bytes,
+                         "family_ms": {names[k]: float(fam_ms[k]) for k in range(4) if fam_n[k] > 0},
+                         "visits": {"bih_branch": stl.visits_bih, "prim_tests": stl.tests_prim, "bvh_branch": stl.visits_bvh,
+                                    "tri_tests": stl.tests_tri, "instance": stl.visits_instance}},
+            "wall_s_timed_region": t_wall,
+        }
+        if setup:
+            res["scene_setup"] = setup
+        if with_cpu and world == 1:
+            threads = os.cpu_count() or 1
+            r = cpu_sample(G, cfg, fs, cam, recurs, cpu_seconds, threads)
+            res["cpu_baseline"] = cpu_baseline_entry(r, threads)
+            res["cpu_baseline"]["ref_visits_per_ray"] = {"bih_branch": r["stats"]["bih_branch"] / max(1, r["rays"]),
+                                                         "bvh_branch": r["stats"]["bvh_branch"] / max(1, r["rays"])}
+    del rdr
+    scene.close()
+    b.close()
+    torch.cuda.empty_cache()
+    return res
 
 
 def main():
@@ -180,9 +400,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="glome_b200")
+    ap.add_argument("--config", type=int, default=HEADLINE, help="headline config id (1..5 = configs[0..4]); default 5")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--all-configs", action="store_true",
-                    help="also time the other BASELINE.json configs (printed to stderr as a table; the JSON line is unchanged)")
+    ap.add_argument("--no-all-configs", action="store_true", help="skip the per-config `configs` object (N = 1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -194,235 +414,56 @@ def main():
     import torch.distributed as dist
     import glome_b200 as G
     from glome_b200 import _lib as L
-    from glome_b200.dist import ShardedRenderer
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    X = Ctx()
+    X.G, X.L, X.torch, X.dist, X.np = G, L, torch, dist, np
+    X.rank = int(os.environ.get("RANK", "0"))
+    X.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    X.world = int(os.environ.get("WORLD_SIZE", "1"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(X.local_rank)
+    if X.world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", X.local_rank))
+    X.flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.int32, device="cuda")
 
-    # scene set-up (timed separately by the reference too, Glome.hs:448-453): the bih is built on this rank's GPU;
-    # rank 0 of a 1-GPU run also times the host builder on the same boxes for the report
-    setup = None
-    if rank == 0 and world == 1:
-        hb = build_scene(G)[0]
-        host_ms = hb.last_build_ms()[3]
-        hb.close()
-    if rank == 0 and world == 1:
-        build_scene(G, local_rank)[0].close()  # untimed first build: context, module load, first cudaMalloc of the work space
-    b, fs, cam, recurs = build_scene(G, local_rank)
-    gm = b.last_build_ms()
-    if rank == 0 and world == 1:
-        setup = {"bih_items": N_SPHERES, "bih_build_gpu_ms": {"h2d": gm[0], "device": gm[1], "d2h": gm[2], "wall": gm[3]},
-                 "bih_build_host_ms": host_ms, "host_threads": os.cpu_count(),
-                 "note": "same tree either way (tests/test_gpu_build.py); not part of the timed frame"}
-    scene = G.Scene(fs, local_rank)
-    # N > 1: the gathered framebuffer is the packed 0x00RRGGBB image (what blitTile writes, Glome.hs:353-358)
-    rdr = ShardedRenderer(scene, cam, WIDTH, HEIGHT, L.MODE_ONE_RAY, recurs, rank=rank, world=world, want_tcolor=False)
-    flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.int32, device="cuda")
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- warm-up ----
-    for _ in range(args.warmup):
-        rdr.render_frame_dev()
-    barrier()
-    # rays per frame (whole job) from the kernels' own counters
-    rdr.render_frame_dev(want_stats=True)
-    st = rdr.last_stats
-    counts = torch.tensor([st.rays_primary, st.rays_shadow, st.rays_secondary, st.visits_bih, st.tests_prim,
-                           st.visits_bvh, st.tests_tri, st.overflow_rays], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(counts)
-    c = counts.tolist()
-    rays_frame = c[0] + c[1] + c[2]
-    barrier()
-
-    # ---- timed: device-resident (value) ----
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(X.local_rank) if X.rank == 0 else None
     if sampler:
         sampler.start()
-    rdr.launches = 0
-    evs = []
-    kernel_ms = []
-    barrier()
-    t_wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        flush.fill_(1)  # L2 flush, outside the event pair
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        rdr.render_frame_dev()
-        e1.record()
-        evs.append((e0, e1))
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    step_ms = [a.elapsed_time(bb) for a, bb in evs]
-    tot = torch.tensor([sum(step_ms)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-    total_ms = tot.item()
-    launches = rdr.launches
-    ms_per_step = total_ms / args.steps
-    value = rays_frame / (ms_per_step * 1e-3) / 1e6
-
-    # ---- timed: the dominant kernel alone (roofline): the persistent BIH traversal kernel, closest-hit + any-hit
-    # launches of one frame, bracketed by CUDA events on the launching stream inside glome_render_dev ----
-    opts1 = G.render_opts(mode=L.MODE_ONE_RAY, recurs=recurs, tile_first=rank, tile_stride=world)
-    kt, tt, tl = [], [], 0
-    for _ in range(min(args.steps, 10)):
-        flush.fill_(1)
-        torch.cuda.synchronize()
-        s1 = scene.render_ptr(cam, WIDTH, HEIGHT, opts1, rdr.tcolor.data_ptr(), 0, dev=True,
-                              stream=torch.cuda.current_stream().cuda_stream)
-        kt.append(s1.kernel_ms)
-        tt.append(s1.traverse_ms)
-        tl = s1.traverse_launches
-    kern_ms = float(np.mean(kt))
-    trav_ms = float(np.mean(tt))
-
-    # ---- timed: end to end through the C-ABI with host buffers (e2e) ----
-    e2e_ms = []
-    pinned = torch.zeros((HEIGHT, WIDTH), dtype=torch.int32).pin_memory()
-    opts_e2e = G.render_opts(mode=L.MODE_ONE_RAY, recurs=recurs)
-    barrier()
-    for i in range(args.warmup + args.steps):
-        flush.fill_(1)
-        barrier()
-        t0 = time.perf_counter()
-        if world == 1:
-            scene.render_ptr(cam, WIDTH, HEIGHT, opts_e2e, None, pinned.data_ptr(), dev=False)
-        else:
-            rdr.render_frame_host(copy_on=0)
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) * 1e3
-        if i >= args.warmup:
-            e2e_ms.append(dt)
-    e2e_t = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_ms_per_step = e2e_t.item() / args.steps
-    e2e_value = rays_frame / (e2e_ms_per_step * 1e-3) / 1e6
+    head = measure(X, args.config, args.steps, args.warmup, not args.no_cpu_baseline, 10.0, setup_report=True)
     clocks = sampler.stop() if sampler else None
 
-    if rank == 0:
-        peaks, which = measured_peaks()
-        # algorithmic bytes of the traversal launches of one frame on this rank: BIH branch 32 B,
-        # sphere record 32 B, BVH branch 128 B, triangle 32 B Tri + 72 B vertices, 24 B hit record out per ray
-        stl = rdr.last_stats
-        rays_rank = stl.rays_primary + stl.rays_shadow
-        alg_bytes = (stl.visits_bih * 32 + stl.tests_prim * 32 + stl.visits_bvh * 128 + stl.tests_tri * 104 + rays_rank * 24)
-        achieved = alg_bytes / (trav_ms * 1e-3) / 1e9
-        traffic = None
-        try:  # DRAM bytes of the same launches from the committed ncu capture (profiles/), N=1 only
-            if world == 1:
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["dram_bytes_per_frame_traversal"]
-        except Exception:
-            pass
-        own = None
-        try:  # own-measured L2 / FP64 denominators (bench/peaks.cu on this pool's B200)
-            own = json.load(open(os.path.join(ROOT, "profiles", "own_peaks.json")))
-        except Exception:
-            pass
+    others = {}
+    if X.world == 1 and not args.no_all_configs:
+        for cfg in sorted(CFG):
+            if cfg == args.config:
+                continue
+            try:
+                others[CFG[cfg]["key"]] = measure(X, cfg, min(args.steps, 10), 3, not args.no_cpu_baseline, 4.0)
+            except Exception as e:  # a failing side config must not take the headline line with it
+                others[CFG[cfg]["key"]] = {"error": repr(e)}
+
+    if X.rank == 0:
         line = {
-            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world),
-            "fps": 1000.0 / ms_per_step,
-            "rays_per_frame": {"primary": c[0], "shadow": c[1], "secondary": c[2], "overflow": c[7]},
-            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 160,
-                    "d2h_bytes_per_step": WIDTH * HEIGHT * 4, "ms_per_step": e2e_ms_per_step,
-                    "fps": 1000.0 / e2e_ms_per_step,
-                    "api": "glome_render (C-ABI, host buffers): camera+options in, 0x00RRGGBB frame to pinned host memory"
-                           if world == 1 else "ShardedRenderer.render_frame_host: render + NCCL all-gather on every rank + D2H of the frame on rank 0 (the displaying rank)"},
-            "gpu_launches": launches,
-            "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": which,
-                         "kernel": "k_bih_traverse (persistent BIH traversal): %d launches per frame, closest-hit + any-hit" % tl,
-                         "kernel_ms": trav_ms, "share_of_step": trav_ms / kern_ms, "frame_kernels_ms": kern_ms,
-                         "algorithmic_bytes_per_launch": alg_bytes,
-                         "visits": {"bih_branch": stl.visits_bih, "sphere_tests": stl.tests_prim},
-                         "note": "working set (~96 MB) is L2-resident: see profiles/ for L2 and issue-slot figures"},
-            "wall_s_timed_region": t_wall,
+            "metric": "Mrays/s", "value": head["value"], "unit": "Mrays/s", "n_gpus": X.world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.config, X.world),
+            "fps": head["fps"], "rays_per_frame": head["rays_per_frame"], "frame_hash": head["frame_hash"],
+            "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": clocks, "roofline": head["roofline"],
+            "wall_s_timed_region": head["wall_s_timed_region"],
         }
-        if own:
-            # the working set is L2-resident, so the meaningful memory ceiling is the L2's: algorithmic bytes per second
-            # against the own-measured L2 streaming-read bandwidth (an upper bound on what reaches L2: L1 hits ~50 %)
-            line["roofline"]["l2_own_measured"] = {"achieved": achieved, "peak": own["l2_read_gbs"], "unit": "GB/s",
-                                                   "frac": achieved / own["l2_read_gbs"],
-                                                   "fp64_nofma_peak_gops": own["fp64_nofma_gops"],
-                                                   "l2_dependent_load_cycles": own["l2_dependent_load_cycles"],
-                                                   "source": "profiles/own_peaks.json (bench/peaks.cu)"}
-        if setup:
-            line["scene_setup"] = setup
-        if not args.no_cpu_baseline and world == 1:
-            threads = os.cpu_count() or 1
-            r = cpu_sample(G, fs, cam, recurs, 12.0, threads)
-            line["cpu_baseline"] = {
-                "value": r["rays"] / r["seconds"] / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
-                "sample": "%d of %d tiles (strided over the frame), %.1f s; C++ restatement of GlomeTrace (oracle/), "
-                          "not GHC: no Haskell toolchain in this image" % (r["tiles"], r["ntiles"], r["seconds"]),
-                "ref_visits_per_ray": {"bih_branch": r["stats"]["bih_branch"] / max(1, r["rays"]),
-                                       "sphere_tests": r["stats"]["node_1"] / max(1, r["rays"])}}
-        if args.all_configs and world == 1:
-            all_configs_table(G, L, not args.no_cpu_baseline)
+        for k in ("scene_setup", "cpu_baseline"):
+            if k in head:
+                line[k] = head[k]
+        if X.world == 1 and not args.no_all_configs:
+            cf = dict(others)
+            cf[CFG[args.config]["key"]] = {k: head[k] for k in head if k not in ("scene_setup",)}
+            line["configs"] = {k: cf[k] for k in sorted(cf)}
         print(json.dumps(line))
-    if world > 1:
+    if X.world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
-
-
-def all_configs_table(G, L, with_cpu):
-    """The other BASELINE.json configs (parity-test cases, not bench lines): device time per frame on one GPU and,
-    optionally, the oracle on the host cores for the same frame (bounded sample of tiles)."""
-    import numpy as np
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    rows = [("1 TestScene 720x480, 1 ray/px", 1, 0, 720, 480, L.MODE_ONE_RAY),
-            ("1 TestScene 720x480, adaptive AA", 1, 0, 720, 480, L.MODE_ADAPTIVE_AA),
-            ("2 1M spheres 1920x1080, 1 ray/px", 2, 1000000, 1920, 1080, L.MODE_ONE_RAY),
-            ("2 1M spheres 720x480, adaptive AA", 2, 1000000, 720, 480, L.MODE_ADAPTIVE_AA),
-            ("3 2M-tri mesh 1920x1080, 1 ray/px", 3, 2000000, 1920, 1080, L.MODE_ONE_RAY),
-            ("4 CSG grid 1280x720, recurs 5", 4, 16, 1280, 720, L.MODE_ONE_RAY),
-            ("5 2M-tri mesh 3840x2160, adaptive AA", 5, 2000000, 3840, 2160, L.MODE_ADAPTIVE_AA)]
-    print("%-40s %10s %8s %12s %12s %10s" % ("config", "ms/frame", "fps", "Mrays/frame", "GPU Mrays/s", "CPU Mrays/s"), file=sys.stderr)
-    for name, cfg, n, w, h, mode in rows:
-        b = G.SceneBuilder()
-        root, cam, rec = b.config_scene(cfg, n)
-        fs = b.flatten(root)
-        sc = G.Scene(fs)
-        opts = G.render_opts(mode=mode, recurs=rec)
-        ms = []
-        for i in range(6):
-            tc, _, st = sc.render(cam, w, h, opts)
-            if i >= 2:
-                ms.append(st.kernel_ms)
-        rays = st.rays_primary + st.rays_shadow + st.rays_secondary
-        cpu = ""
-        if with_cpu:
-            import oracle as O
-            osc = O.OracleScene(fs)
-            nt = len(O.tile_rects(w, h, 65))
-            k = min(nt, 48)
-            o2 = G.render_opts(mode=mode, recurs=rec, tile_first=0, tile_stride=max(1, nt // k))
-            frame = np.zeros((h, w, 5))
-            t0 = time.perf_counter()
-            osc.render(cam, w, h, o2, threads=os.cpu_count() or 1, max_tiles=k, out=frame)
-            dt = time.perf_counter() - t0
-            so = osc.stats()
-            cpu = "%.2f" % ((so["rays_primary"] + so["rays_shadow"] + so["rays_secondary"]) / dt / 1e6)
-            osc.close()
-        m = float(np.median(ms))
-        print("%-40s %10.3f %8.1f %12.3f %12.1f %10s" % (name, m, 1000.0 / m, rays / 1e6, rays / (m * 1e-3) / 1e6, cpu),
-              file=sys.stderr)
-        sc.close()
 
 
 if __name__ == "__main__":

@@ -85,7 +85,8 @@ class GlomeRenderStats(C.Structure):
                 ("overflow_rays", C.c_int64), ("perlin_range", C.c_int64), ("kernel_ms", C.c_double),
                 ("launches", C.c_int32), ("reserved", C.c_int32), ("visits_bih", C.c_int64), ("tests_prim", C.c_int64),
                 ("visits_bvh", C.c_int64), ("tests_tri", C.c_int64), ("traverse_ms", C.c_double),
-                ("traverse_launches", C.c_int64)]
+                ("traverse_launches", C.c_int64), ("family_ms", C.c_double * 4), ("family_launches", C.c_int64 * 4),
+                ("visits_instance", C.c_int64), ("csg_steps", C.c_int64)]
 
 
 assert C.sizeof(GlomeHit) == 144 and C.sizeof(GlomeBihNode) == 32 and C.sizeof(GlomeBvhNode) == 128

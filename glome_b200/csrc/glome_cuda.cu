@@ -17,17 +17,21 @@
 #include <thread>
 #include <vector>
 
+#include <mutex>
+
 #include "glome_device.cuh"
+#include "glome_gen.cuh"
+#include "glome_tagmap.h"
 #include "glome_wave.cuh"
 
 #ifndef GLOME_AA_SPEC_RATIO
 #define GLOME_AA_SPEC_RATIO 0.6  /* flat scenes: speculate AA passes 1-4 when the last frame traced this share of the pixel centres */
 #endif
 #ifndef GEN_THREADS
-#define GEN_THREADS 64
+#define GEN_THREADS 128
 #endif
 #ifndef GEN_MINBLOCKS
-#define GEN_MINBLOCKS 10
+#define GEN_MINBLOCKS 4
 #endif
 
 using namespace gdev;
@@ -123,15 +127,16 @@ __device__ __forceinline__ uint32_t rgbf(Flt r, Flt g, Flt b) {                 
     return R * 65536u + G * 256u + B;
 }
 
-struct DevStats {  // accumulated with atomics
-    unsigned long long primary, shadow, secondary, overflow, perlin_range, bih, prim, bvh, tri;
+struct DevStats {  // accumulated with atomics; the first nine are gwave's stats slots
+    unsigned long long primary, shadow, secondary, overflow, perlin_range, bih, prim, bvh, tri, inst, csg;
 };
 
-__device__ __forceinline__ void flush_counters(DevStats* st, unsigned int primary, const RayCounters& rc, unsigned int ovf) {
+__device__ __forceinline__ void flush_counters(DevStats* st, unsigned int primary, const RayCounters& rc, unsigned int ovf,
+                                               unsigned int inst = 0, unsigned int csg = 0) {
     // warp-reduce then one atomic per warp and counter
-    unsigned int vals[9] = {primary, rc.shadow, rc.secondary, ovf, rc.perlin_range, rc.cnt.bih, rc.cnt.prim, rc.cnt.bvh, rc.cnt.tri};
+    unsigned int vals[11] = {primary, rc.shadow, rc.secondary, ovf, rc.perlin_range, rc.cnt.bih, rc.cnt.prim, rc.cnt.bvh, rc.cnt.tri, inst, csg};
 #pragma unroll
-    for (int k = 0; k < 9; k++) {
+    for (int k = 0; k < 11; k++) {
         unsigned int v = vals[k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -147,7 +152,15 @@ __device__ __forceinline__ void flush_counters(DevStats* st, unsigned int primar
         if (vals[6]) atomicAdd(&st->prim, (unsigned long long)vals[6]);
         if (vals[7]) atomicAdd(&st->bvh, (unsigned long long)vals[7]);
         if (vals[8]) atomicAdd(&st->tri, (unsigned long long)vals[8]);
+        if (vals[9]) atomicAdd(&st->inst, (unsigned long long)vals[9]);
+        if (vals[10]) atomicAdd(&st->csg, (unsigned long long)vals[10]);
     }
+}
+__device__ __forceinline__ void flush_gcnt(DevStats* st, unsigned int primary, const ggen::GCnt& c, unsigned int ovf) {
+    RayCounters rc;
+    rc.shadow = c.shadow; rc.secondary = c.secondary; rc.perlin_range = c.perlin;
+    rc.cnt.bih = c.bih; rc.cnt.prim = c.prim; rc.cnt.bvh = c.bvh; rc.cnt.tri = c.tri;
+    flush_counters(st, primary, rc, ovf, c.inst, c.csg);
 }
 
 __device__ __forceinline__ void hit_out(const Hit& h, GlomeHit* o) {
@@ -179,63 +192,105 @@ __device__ __forceinline__ Ray ld_ray(const double* __restrict__ rays, long long
 // ---------------------------------------------------------------------------------------------
 // batch query kernels (parity surfaces)
 // ---------------------------------------------------------------------------------------------
+// GEN = false: flat-class scenes (three fixed levels, glome_device.cuh); GEN = true: any scene graph, evaluated by the
+// iterative machine of glome_gen.cuh (its stacks are this thread's local memory; no device recursion anywhere).
 template <bool GEN>
 __global__ void __launch_bounds__(128) k_rayint_batch(DScene S, long long n, const double* __restrict__ rays,
                                                       const double* __restrict__ tmax, int stride, GlomeHit* __restrict__ out) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        Hit h;
-        rayint_scene<GEN>(S, S.root, ld_ray(rays, i), tmax[stride ? i : 0], h);
-        hit_out(h, out + i);
+        if constexpr (GEN) {
+            ggen::QVM vm;
+            ggen::GCnt c;
+            ggen::gcnt_clear(c);
+            ggen::gq_query(S, vm, S.root, ld_ray(rays, i), tmax[stride ? i : 0], false, c);
+            ggen::ghit_out(S, vm.slot[0], out + i);
+        } else {
+            Hit h;
+            rayint_scene_flat(S, S.root, ld_ray(rays, i), tmax[stride ? i : 0], h);
+            hit_out(h, out + i);
+        }
     }
 }
 template <bool GEN>
 __global__ void __launch_bounds__(128) k_shadow_batch(DScene S, long long n, const double* __restrict__ rays,
                                                       const double* __restrict__ tmax, int stride, uint8_t* __restrict__ out) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        out[i] = shadow_scene<GEN>(S, S.root, ld_ray(rays, i), tmax[stride ? i : 0]) ? 1 : 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if constexpr (GEN) {
+            ggen::QVM vm;
+            ggen::GCnt c;
+            ggen::gcnt_clear(c);
+            out[i] = ggen::gq_query(S, vm, S.root, ld_ray(rays, i), tmax[stride ? i : 0], true, c) ? 1 : 0;
+        } else out[i] = shadow_scene_flat(S, S.root, ld_ray(rays, i), tmax[stride ? i : 0]) ? 1 : 0;
+    }
 }
 __global__ void __launch_bounds__(128) k_inside_batch(DScene S, long long n, const double* __restrict__ pts,
                                                       uint8_t* __restrict__ out) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        out[i] = inside_node(S, S.root, vec(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2])) ? 1 : 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        int ovf = 0;
+        out[i] = ggen::gq_inside(S, S.root, vec(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]), &ovf) ? 1 : 0;
+    }
 }
 // the pick query's variant: also the TraceResult's tag list, n*(2+16) int32 = {count, overflow, tags...}
 template <bool GEN>
-__global__ void __launch_bounds__(128) k_trace_tags(DScene S, long long n, const double* __restrict__ rays,
-                                                    const double* __restrict__ tmax, int stride, int recurs,
-                                                    GlomeHit* __restrict__ hits, int* __restrict__ tags) {
-    RayCounters rc = {0, 0, 0, {0, 0, 0, 0}};
+__global__ void __launch_bounds__(64) k_trace_tags(DScene S, long long n, const double* __restrict__ rays,
+                                                   const double* __restrict__ tmax, int stride, int recurs,
+                                                   GlomeHit* __restrict__ hits, int* __restrict__ tags) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        ColorA c;
-        Hit h;
-        TagList tl;
-        tl_clear(tl);
-        trace<GEN, TagList*>(S, 0, S.root, ld_ray(rays, i), tmax[stride ? i : 0], recurs, c, h, rc, &tl);
-        if (hits) hit_out(h, hits + i);
-        int* o = tags + (2 + GDEV_TAGLIST_CAP) * i;
-        o[0] = tl.n; o[1] = tl.overflow;
-        for (int k = 0; k < GDEV_TAGLIST_CAP; k++) o[2 + k] = k < tl.n ? tl.v[k] : -1;
+        int* o = tags + (2 + 16) * i;
+        if constexpr (GEN) {
+            ggen::SHM sh;
+            ggen::GCnt c;
+            ggen::gcnt_clear(c);
+            ggen::TagArena ta;
+            ColorA col;
+            int fl = 0;
+            ggen::gs_trace<true>(S, sh, 0, S.root, ld_ray(rays, i), tmax[stride ? i : 0], recurs, col, c, fl, &ta);
+            if (hits) { ggen::ghit_out(S, sh.tf[0].ri, hits + i); hits[i].flags |= fl; }
+            o[0] = ta.n; o[1] = ta.overflow || ta.n > 16;
+            for (int k = 0; k < 16; k++) o[2 + k] = k < ta.n ? S.tagvals[ta.v[k]] : -1;
+        } else {
+            RayCounters rc = {0, 0, 0, {0, 0, 0, 0}};
+            ColorA col;
+            Hit h;
+            trace_flat(S, 0, S.root, ld_ray(rays, i), tmax[stride ? i : 0], recurs, col, h, rc);
+            if (hits) hit_out(h, hits + i);
+            const int nt = h.hit ? h.tag.n : 0;  // ts is empty for Surface materials: `ts ++ tags` = the hit's tag stack
+            o[0] = nt; o[1] = 0;
+            for (int k = 0; k < 16; k++) o[2 + k] = k < nt ? h.tag.v[k] : -1;
+        }
     }
 }
 template <bool GEN>
-__global__ void __launch_bounds__(128) k_trace_batch(DScene S, long long n, const double* __restrict__ rays,
-                                                     const double* __restrict__ tmax, int stride, int recurs,
-                                                     double* __restrict__ rgba, double* __restrict__ depth,
-                                                     GlomeHit* __restrict__ hits, DevStats* st) {
+__global__ void __launch_bounds__(GEN ? 64 : 128) k_trace_batch(DScene S, long long n, const double* __restrict__ rays,
+                                                                const double* __restrict__ tmax, int stride, int recurs,
+                                                                double* __restrict__ rgba, double* __restrict__ depth,
+                                                                GlomeHit* __restrict__ hits, DevStats* st) {
     RayCounters rc = {0, 0, 0, {0, 0, 0, 0}};
+    ggen::GCnt gc;
+    ggen::gcnt_clear(gc);
     unsigned int ovf = 0, prim = 0;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         ColorA c;
-        Hit h;
-        trace<GEN>(S, 0, S.root, ld_ray(rays, i), tmax[stride ? i : 0], recurs, c, h, rc);
+        if constexpr (GEN) {
+            ggen::SHM sh;
+            int fl = 0;
+            ggen::gs_trace<false>(S, sh, 0, S.root, ld_ray(rays, i), tmax[stride ? i : 0], recurs, c, gc, fl, nullptr);
+            depth[i] = ggen::ghit_depth(sh.tf[0].ri);
+            if (hits) { ggen::ghit_out(S, sh.tf[0].ri, hits + i); hits[i].flags |= fl; }
+            if (fl) ovf++;
+        } else {
+            Hit h;
+            trace_flat(S, 0, S.root, ld_ray(rays, i), tmax[stride ? i : 0], recurs, c, h, rc);
+            depth[i] = ridepth(h);
+            if (hits) hit_out(h, hits + i);
+            if (h.flags) ovf++;
+        }
         rgba[4 * i] = c.r; rgba[4 * i + 1] = c.g; rgba[4 * i + 2] = c.b; rgba[4 * i + 3] = c.a;
-        depth[i] = ridepth(h);
-        if (hits) hit_out(h, hits + i);
-        if (h.flags) ovf++;
         prim++;
     }
     __syncwarp();
-    flush_counters(st, prim, rc, ovf);
+    if constexpr (GEN) flush_gcnt(st, prim, gc, ovf);
+    else flush_counters(st, prim, rc, ovf);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -264,6 +319,8 @@ template <bool GEN, int MODE>
 __global__ void __launch_bounds__(GEN ? GEN_THREADS : 128, GEN ? GEN_MINBLOCKS : 1) k_trace_samples(DScene S, TraceParams P) {
     const int lane = threadIdx.x & 31;
     RayCounters rc = {0, 0, 0, {0, 0, 0, 0}};
+    ggen::GCnt gc;
+    ggen::gcnt_clear(gc);
     unsigned int ovf = 0, nprim = 0;
     const long long total = (MODE == 0) ? (long long)P.n_sel * P.g.slots_per_tile : (long long)(*P.queue_count);
     // Rays per warp-chunk.  The general interpreter serialises divergent lanes, so when a wave has too few samples
@@ -297,12 +354,22 @@ __global__ void __launch_bounds__(GEN ? GEN_THREADS : 128, GEN ? GEN_MINBLOCKS :
             if (MODE == 5) getCoordsf(P.g.width, P.g.height, (Flt)x + 0.5, (Flt)y + 0.5, xc, yc);
             else getCoordsf(P.g.width, P.g.height, (Flt)x, (Flt)y, xc, yc);
             ColorA c;
-            Hit h;
-            trace<GEN>(S, 0, S.root, camera_ray(P.cam, xc, yc), GLM_INFINITY, P.recurs, c, h, rc);
+            Flt hd;
+            if constexpr (GEN) {
+                ggen::SHM sh;
+                int fl = 0;
+                ggen::gs_trace<false>(S, sh, 0, S.root, camera_ray(P.cam, xc, yc), GLM_INFINITY, P.recurs, c, gc, fl, nullptr);
+                hd = ggen::ghit_depth(sh.tf[0].ri);
+                if (fl) ovf++;
+            } else {
+                Hit h;
+                trace_flat(S, 0, S.root, camera_ray(P.cam, xc, yc), GLM_INFINITY, P.recurs, c, h, rc);
+                hd = ridepth(h);
+                if (h.flags) ovf++;
+            }
             nprim++;
-            if (h.flags) ovf++;
             TC col;
-            col.r = c.r; col.g = c.g; col.b = c.b; col.a = c.a; col.d = ridepth(h);
+            col.r = c.r; col.g = c.g; col.b = c.b; col.a = c.a; col.d = hd;
             size_t pix = (size_t)y * P.g.width + x;
             if (MODE == 0) {
                 if (P.tint) col.r = col.r + (col.d / 400);  // Glome.hs:174
@@ -320,7 +387,8 @@ __global__ void __launch_bounds__(GEN ? GEN_THREADS : 128, GEN ? GEN_MINBLOCKS :
         }
     }
     __syncwarp();
-    flush_counters(P.st, nprim, rc, ovf);
+    if constexpr (GEN) flush_gcnt(P.st, nprim, gc, ovf);
+    else flush_counters(P.st, nprim, rc, ovf);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -446,8 +514,10 @@ struct GlomeScene {
     int sm_count;
     DScene d;
     std::vector<void*> bufs;
-    // render workspace (grown on demand)
-    double* v; double* v2; uint32_t* rgb8; size_t ws_pix;
+    // render workspace (grown on demand; one capacity per buffer: glome_render and glome_render_dev size them separately)
+    double* v; size_t v_pix;
+    double* v2; size_t v2_pix;
+    uint32_t* rgb8; size_t rgb8_pix;
     double* spec; size_t spec_pix;
     int* queue; size_t queue_cap;
     int* queue_count; unsigned int* work_counter; DevStats* stats;
@@ -455,7 +525,10 @@ struct GlomeScene {
     void* bw[4]; size_t bw_cap[4];
     cudaEvent_t ev0, ev1;
     int launches;
-    size_t stack_bytes;
+    // launch geometry of the persistent kernels on this device, computed once at creation
+    int g_bih[4], g_bvh, g_gen[3], g_flat[3];
+    // environment switches (A/B runs), read once at creation: never in the frame path
+    int env_no_speculate, env_aa_speculate, env_gen_chunk;
     // wavefront pipeline (flat scenes)
     bool use_wave;
     std::vector<gwave::Seg> segs;
@@ -467,6 +540,7 @@ struct GlomeScene {
     unsigned int* w_counters;  // one work counter per persistent launch of a frame
     int w_counter_next;
     std::vector<cudaEvent_t> tev;  // start/stop pairs around the traversal kernels of the last timed frame
+    std::vector<int> tev_family;   // kernel family of each pair (GlomeRenderStats.family_ms)
     int tev_used;
     bool time_traversal;
     int n_scene_lights;
@@ -555,20 +629,106 @@ static int validate(const GlomeFlatScene* d) {
                 bad = n.a < 0 || n.a >= d->n_nodes || n.b < 0 || n.b >= d->n_nodes; break;
             case GLOME_TEX: bad = n.a < 0 || n.a >= d->n_nodes || n.b < 0 || n.b >= d->n_textures; break;
             case GLOME_TAG: case GLOME_NOSHADOW: case GLOME_ONLYSHADOW: bad = n.a < 0 || n.a >= d->n_nodes; break;
-            case GLOME_BIH: bad = n.b < 0 || (long long)n.b + 6 > d->n_dpool || (n.a >= 0 && n.a >= d->n_bihnodes); break;
-            case GLOME_MESH: bad = n.a < 0 || (long long)n.a + 12 > d->n_ipool; break;
+            case GLOME_BIH: bad = n.b < 0 || (long long)n.b + 6 > d->n_dpool || (n.b & 1) || (n.a >= 0 && n.a >= d->n_bihnodes); break;
+            case GLOME_MESH: {
+                bad = n.a < 0 || (long long)n.a + 12 > d->n_ipool;
+                if (!bad) {
+                    const GlomeMeshHeader* h = reinterpret_cast<const GlomeMeshHeader*>(d->ipool + n.a);
+                    bad = h->bb_off < 0 || (long long)h->bb_off + 6 > d->n_dpool || (h->bb_off & 1) || h->ntris < 0 || h->nverts < 0 ||
+                          h->verts_off < 0 || (long long)h->verts_off + 3LL * h->nverts > d->n_dpool ||
+                          h->norms_off < 0 || (long long)h->norms_off + 3LL * h->nnorms > d->n_dpool ||
+                          h->tris_off < 0 || (h->tris_off & 3) || (long long)h->tris_off + 8LL * h->ntris > d->n_ipool ||
+                          h->texs_off < 0 || (long long)h->texs_off + h->ntexs > d->n_ipool ||
+                          h->tags_off < 0 || (long long)h->tags_off + h->ntags > d->n_ipool ||
+                          (h->root >= 0 && h->root >= d->n_bvhnodes) || (h->root < 0 && ~h->root >= d->n_ipool);
+                }
+                break;
+            }
             case GLOME_VOID: break;
+            case GLOME_SPHERE: bad = n.a < 0 || (long long)n.a + 4 > d->n_dpool || (n.a & 1); break;  // two 16-byte loads
+            case GLOME_TRIANGLE: bad = n.a < 0 || (long long)n.a + 9 > d->n_dpool; break;
+            case GLOME_TRIANGLENORM: bad = n.a < 0 || (long long)n.a + 18 > d->n_dpool; break;
+            case GLOME_BOX: bad = n.a < 0 || (long long)n.a + 6 > d->n_dpool || (n.a & 1); break;
+            case GLOME_PLANE: case GLOME_CONE: bad = n.a < 0 || (long long)n.a + 4 > d->n_dpool; break;
+            case GLOME_DISC: bad = n.a < 0 || (long long)n.a + 7 > d->n_dpool; break;
+            case GLOME_CYLINDER: bad = n.a < 0 || (long long)n.a + 3 > d->n_dpool; break;
             default: bad = n.a < 0 || n.a >= d->n_dpool; break;
         }
         if (bad) { g_err = "FlatScene: node " + std::to_string(i) + " has out-of-range payload"; return GLOME_EINVAL; }
     }
-    if (d->n_lights > 0 && d->n_lightsets > 0) {
-        for (int i = 0; i < d->n_lightsets; i++)
-            if (d->lightsets[2 * i] < 0 || d->lightsets[2 * i] + d->lightsets[2 * i + 1] > d->n_lights ||
-                d->lightsets[2 * i + 1] > GDEV_MAX_LIGHTS) { g_err = "FlatScene: bad light set"; return GLOME_EINVAL; }
+    // BIH / BVH child refs, leaf ranges
+    for (int i = 0; i < d->n_bihnodes; i++) {
+        const GlomeBihNode& b = d->bihnodes[i];
+        if (b.axis < 0 || b.axis > 2) { g_err = "FlatScene: BIH node " + std::to_string(i) + " has a bad axis"; return GLOME_EINVAL; }
+        for (int c = 0; c < 2; c++) {
+            int32_t ref = c ? b.right : b.left;
+            bool bad;
+            if (ref >= 0) bad = ref >= d->n_bihnodes;
+            else {
+                int32_t k = ~ref;
+                if ((k & 7) != 7) bad = (long long)(k >> 3) + (k & 7) > d->n_nodes;
+                else bad = (long long)(k >> 3) + 2 > d->n_ipool || d->ipool[k >> 3] < 0 || d->ipool[(k >> 3) + 1] < 0 ||
+                           (long long)d->ipool[k >> 3] + d->ipool[(k >> 3) + 1] > d->n_nodes;
+            }
+            if (bad) { g_err = "FlatScene: BIH node " + std::to_string(i) + " has an out-of-range child"; return GLOME_EINVAL; }
+        }
     }
+    for (int i = 0; i < d->n_bvhnodes; i++) {
+        const GlomeBvhNode& b = d->bvhnodes[i];
+        for (int c = 0; c < 2; c++) {
+            int32_t ref = c ? b.right : b.left;
+            bool bad = ref >= 0 ? ref >= d->n_bvhnodes : (~ref >= d->n_ipool || (long long)~ref + 1 + d->ipool[~ref] > d->n_ipool);
+            if (bad) { g_err = "FlatScene: BVH node " + std::to_string(i) + " has an out-of-range child"; return GLOME_EINVAL; }
+        }
+    }
+    for (int i = 0; i < d->n_textures; i++) {
+        const GlomeTexture& t = d->textures[i];
+        bool bad = t.kind < GLOME_TEX_UNIFORM || t.kind > GLOME_TEX_PERLIN_BLEND || t.a < 0 || t.a >= d->n_materials ||
+                   (t.kind != GLOME_TEX_UNIFORM && (t.b < 0 || t.b >= d->n_materials));
+        if (bad) { g_err = "FlatScene: texture " + std::to_string(i) + " names a bad material"; return GLOME_EINVAL; }
+    }
+    for (int i = 0; i < d->n_materials; i++) {
+        const GlomeMaterial& m = d->materials[i];
+        bool bad = false;
+        switch (m.kind) {
+            case GLOME_MAT_SURFACE: case GLOME_MAT_REFLECT: case GLOME_MAT_REFRACT: break;
+            case GLOME_MAT_WARP:
+                bad = m.a < 0 || m.a >= d->n_nodes || m.b < 0 || m.b >= d->n_nodes || m.c < 0 ||
+                      m.c >= (d->n_lightsets > 0 ? d->n_lightsets : 1) || m.d < 0 || (long long)m.d + 24 > d->n_dpool;
+                break;
+            case GLOME_MAT_ADDITIVE:
+                bad = m.b < 0 || m.a < 0 || (long long)m.a + m.b > d->n_ipool;
+                for (int k = 0; !bad && k < m.b; k++) bad = d->ipool[m.a + k] < 0 || d->ipool[m.a + k] >= d->n_materials;
+                break;
+            case GLOME_MAT_BLEND: bad = m.a < 0 || m.a >= d->n_materials || m.b < 0 || m.b >= d->n_materials; break;
+            default: bad = true;
+        }
+        if (bad) { g_err = "FlatScene: material " + std::to_string(i) + " is malformed"; return GLOME_EINVAL; }
+    }
+    for (int i = 0; i < d->n_lights; i++)
+        if (d->lights[i].falloff != 0) { g_err = "FlatScene: unknown light falloff (only 1/(x*x), Shader.hs:23)"; return GLOME_EINVAL; }
+    for (int i = 0; i < d->n_lightsets; i++) {
+        if (d->lightsets[2 * i] < 0 || d->lightsets[2 * i + 1] < 0 || d->lightsets[2 * i] + d->lightsets[2 * i + 1] > d->n_lights) {
+            g_err = "FlatScene: bad light set"; return GLOME_EINVAL;
+        }
+        if (d->lightsets[2 * i + 1] > GDEV_MAX_LIGHTS) { g_err = "FlatScene: more than 64 lights in one light set"; return GLOME_ELIMIT; }
+    }
+    if (d->n_lightsets <= 0 && d->n_lights > GDEV_MAX_LIGHTS) { g_err = "FlatScene: more than 64 lights"; return GLOME_ELIMIT; }
     return GLOME_OK;
 }
+
+template <typename K>
+static int persistent_grid(GlomeScene* s, K kernel, int threads) {
+    int b = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, threads, 0) != cudaSuccess || b < 1) b = 1;
+    return s->sm_count * b;
+}
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+static int scene_create_impl(GlomeScene* s, const GlomeFlatScene* desc, int device);
 
 extern "C" int glome_scene_create(const GlomeFlatScene* desc, int device, GlomeScene** out) {
     if (!out) { g_err = "null out"; return GLOME_EINVAL; }
@@ -582,13 +742,31 @@ extern "C" int glome_scene_create(const GlomeFlatScene* desc, int device, GlomeS
     }
     if (device < 0 || device >= ndev) { g_err = "bad device index"; return GLOME_EINVAL; }
     CK(cudaSetDevice(device));
-    GlomeScene* s = new GlomeScene();
+    GlomeScene* s = nullptr;
+    try {
+        s = new GlomeScene();  // value-initialised: every pointer starts null, so a partial scene can be destroyed
+        rc = scene_create_impl(s, desc, device);
+    } catch (const std::exception& e) {
+        g_err = std::string("glome_scene_create: ") + e.what();
+        rc = GLOME_ECUDA;
+    } catch (...) {
+        g_err = "glome_scene_create: unknown exception";
+        rc = GLOME_ECUDA;
+    }
+    if (rc) {
+        std::string keep = g_err;
+        if (s) glome_scene_destroy(s);
+        g_err = keep;
+        return rc;
+    }
+    *out = s;
+    return GLOME_OK;
+}
+
+static int scene_create_impl(GlomeScene* s, const GlomeFlatScene* desc, int device) {
+    int rc;
     s->device = device;
     s->scene_class = desc->scene_class;
-    s->v = s->v2 = nullptr; s->rgb8 = nullptr; s->ws_pix = 0; s->queue = nullptr; s->queue_cap = 0;
-    s->spec = nullptr; s->spec_pix = 0;
-    for (int i = 0; i < 4; i++) { s->bw[i] = nullptr; s->bw_cap[i] = 0; }
-    s->launches = 0;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     s->sm_count = prop.multiProcessorCount;
@@ -598,10 +776,21 @@ extern "C" int glome_scene_create(const GlomeFlatScene* desc, int device, GlomeS
     std::vector<int32_t> ls;
     if (desc->n_lightsets > 0) ls.assign(desc->lightsets, desc->lightsets + 2 * desc->n_lightsets);
     else { ls.push_back(0); ls.push_back(desc->n_lights); }
-    if ((rc = upload(s, desc->nodes, (size_t)desc->n_nodes, &s->d.nodes))) return rc;
+    if (s->scene_class == GLOME_CLASS_GENERAL) {
+        // the scene-graph machine packs tag ids into 16 bits: upload dense ids and the table that maps them back
+        std::vector<GlomeNode> nodes;
+        std::vector<int32_t> ipool, tagvals;
+        std::string e = glome_tagmap::remap_tags(desc, nodes, ipool, tagvals);
+        if (!e.empty()) { g_err = e; return GLOME_ELIMIT; }
+        if ((rc = upload(s, nodes.data(), nodes.size(), &s->d.nodes))) return rc;
+        if ((rc = upload(s, ipool.data(), ipool.size(), &s->d.ipool))) return rc;
+        if ((rc = upload(s, tagvals.data(), tagvals.size(), &s->d.tagvals))) return rc;
+    } else {
+        if ((rc = upload(s, desc->nodes, (size_t)desc->n_nodes, &s->d.nodes))) return rc;
+        if ((rc = upload(s, desc->ipool, (size_t)desc->n_ipool, &s->d.ipool))) return rc;
+    }
     if ((rc = upload(s, desc->bihnodes, (size_t)desc->n_bihnodes, &s->d.bih))) return rc;
     if ((rc = upload(s, desc->bvhnodes, (size_t)desc->n_bvhnodes, &s->d.bvh))) return rc;
-    if ((rc = upload(s, desc->ipool, (size_t)desc->n_ipool, &s->d.ipool))) return rc;
     if ((rc = upload(s, desc->dpool, (size_t)desc->n_dpool, &s->d.dpool))) return rc;
     if ((rc = upload(s, desc->textures, (size_t)desc->n_textures, &s->d.textures))) return rc;
     if ((rc = upload(s, desc->materials, (size_t)desc->n_materials, &s->d.materials))) return rc;
@@ -612,24 +801,25 @@ extern "C" int glome_scene_create(const GlomeFlatScene* desc, int device, GlomeS
     CK(cudaMalloc((void**)&s->stats, sizeof(DevStats)));
     CK(cudaEventCreate(&s->ev0));
     CK(cudaEventCreate(&s->ev1));
-    // the general interpreter recurses: give its threads a deep stack
-    s->stack_bytes = 0;
-    if (s->scene_class == GLOME_CLASS_GENERAL) {
-        size_t want = 40 * 1024;
-        const char* e = getenv("GLOME_STACK_BYTES");
-        if (e) want = (size_t)atol(e);
-        CK(cudaDeviceSetLimit(cudaLimitStackSize, want));
-        s->stack_bytes = want;
-    }
-    s->use_wave = false;
-    s->segs_dev = nullptr; s->wave_cap = 0;
-    s->w_hit_t = nullptr; s->w_hit_seg = s->w_hit_item = s->w_hit_sub = s->w_hit_flags = nullptr;
-    s->w_surf = nullptr; s->w_occl = nullptr; s->w_squeue = nullptr; s->w_squeue_count = nullptr; s->w_counters = nullptr;
-    s->w_counter_next = 0;
-    s->tev_used = 0; s->time_traversal = false;
     s->n_scene_lights = ls[1];
-    s->aa_counts_host = nullptr; s->aa_valid = false; s->aa_ev = nullptr;
-    s->aa_w = s->aa_h = s->aa_first = s->aa_stride = s->aa_bs = 0;
+    s->env_no_speculate = env_int("GLOME_NO_SPECULATE", 0);
+    s->env_aa_speculate = env_int("GLOME_AA_SPECULATE", -1);
+    s->env_gen_chunk = env_int("GLOME_GEN_CHUNK", 32);
+    if (s->env_gen_chunk < 1) s->env_gen_chunk = 1;
+    if (s->env_gen_chunk > 32) s->env_gen_chunk = 32;
+    // launch geometry of the persistent kernels: once per scene, so that frames issued from several host threads
+    // (glome_multi_render) never race on a lazily initialised cache
+    s->g_bih[0] = persistent_grid(s, gwave::k_bih_traverse<false, false>, GW_THREADS);
+    s->g_bih[1] = persistent_grid(s, gwave::k_bih_traverse<false, true>, GW_THREADS);
+    s->g_bih[2] = persistent_grid(s, gwave::k_bih_traverse<true, false>, GW_THREADS);
+    s->g_bih[3] = persistent_grid(s, gwave::k_bih_traverse<true, true>, GW_THREADS);
+    s->g_bvh = persistent_grid(s, gwave::k_bvh_closest, 128);
+    s->g_gen[0] = persistent_grid(s, k_trace_samples<true, 0>, GEN_THREADS);
+    s->g_gen[1] = persistent_grid(s, k_trace_samples<true, 1>, GEN_THREADS);
+    s->g_gen[2] = persistent_grid(s, k_trace_samples<true, 5>, GEN_THREADS);
+    s->g_flat[0] = persistent_grid(s, k_trace_samples<false, 0>, 128);
+    s->g_flat[1] = persistent_grid(s, k_trace_samples<false, 1>, 128);
+    s->g_flat[2] = persistent_grid(s, k_trace_samples<false, 5>, 128);
     if (s->scene_class == GLOME_CLASS_FLAT && !getenv("GLOME_FLAT_MEGAKERNEL") && build_segments(desc, s->segs) &&
         ls[0] + ls[1] <= 32) {
         CK(cudaMalloc((void**)&s->segs_dev, sizeof(gwave::Seg) * s->segs.size()));
@@ -641,7 +831,6 @@ extern "C" int glome_scene_create(const GlomeFlatScene* desc, int device, GlomeS
                                      (desc->nodes[s->segs[i].node].c & GLOME_BIH_LINEAR_SPHERES) ? 1 : 0);
         s->use_wave = true;
     }
-    *out = s;
     return GLOME_OK;
 }
 
@@ -657,7 +846,8 @@ extern "C" int glome_scene_destroy(GlomeScene* s) {
     cudaFree(s->w_counters);
     if (s->aa_counts_host) cudaFreeHost(s->aa_counts_host);
     if (s->aa_ev) cudaEventDestroy(s->aa_ev);
-    cudaEventDestroy(s->ev0); cudaEventDestroy(s->ev1);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
     for (cudaEvent_t e : s->tev) cudaEventDestroy(e);
     delete s;
     return GLOME_OK;
@@ -733,8 +923,6 @@ extern "C" int glome_inside_batch(GlomeScene* s, int64_t n, const double* pts, u
     if ((rc = grow(s, 0, (size_t)n * 24))) return rc;
     if ((rc = grow(s, 2, (size_t)n))) return rc;
     CK(cudaMemcpy(s->bw[0], pts, (size_t)n * 24, cudaMemcpyHostToDevice));
-    // inside recurses (inside_bih_rec ...): make sure the stack limit is generous for flat scenes too
-    if (s->stack_bytes == 0) { CK(cudaDeviceSetLimit(cudaLimitStackSize, 8 * 1024)); s->stack_bytes = 8 * 1024; }
     k_inside_batch<<<batch_grid(s, n), 128>>>(s->d, n, (const double*)s->bw[0], (uint8_t*)s->bw[2]);
     s->launches++;
     CK(cudaGetLastError());
@@ -761,6 +949,9 @@ static void read_stats(GlomeScene* s, GlomeRenderStats* out, float ms, int launc
     out->tests_prim = (int64_t)h.prim;
     out->visits_bvh = (int64_t)h.bvh;
     out->tests_tri = (int64_t)h.tri;
+    for (int k = 0; k < 4; k++) { out->family_ms[k] = 0; out->family_launches[k] = 0; }
+    out->visits_instance = (int64_t)h.inst;
+    out->csg_steps = (int64_t)h.csg;
 }
 
 extern "C" int glome_trace_batch(GlomeScene* s, int64_t n, const double* rays, const double* tmax, int tmax_stride, int recurs,
@@ -813,7 +1004,7 @@ extern "C" int glome_get_tags(GlomeScene* s, const GlomeCamera* cam, int width, 
     int rc;
     if ((rc = grow(s, 0, 48))) return rc;
     if ((rc = grow(s, 1, 8))) return rc;
-    if ((rc = grow(s, 2, (2 + GDEV_TAGLIST_CAP) * sizeof(int)))) return rc;
+    if ((rc = grow(s, 2, (2 + 16) * sizeof(int)))) return rc;
     if ((rc = grow(s, 3, sizeof(GlomeHit)))) return rc;
     CK(cudaMemcpy(s->bw[0], ray, 48, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(s->bw[1], &tmax, 8, cudaMemcpyHostToDevice));
@@ -823,7 +1014,7 @@ extern "C" int glome_get_tags(GlomeScene* s, const GlomeCamera* cam, int width, 
         k_trace_tags<true><<<1, 128>>>(s->d, 1, (const double*)s->bw[0], (const double*)s->bw[1], 0, recurs, (GlomeHit*)s->bw[3], (int*)s->bw[2]);
     s->launches++;
     CK(cudaGetLastError());
-    int out[2 + GDEV_TAGLIST_CAP];
+    int out[2 + 16];
     GlomeHit h;
     CK(cudaMemcpy(out, s->bw[2], sizeof(out), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(&h, s->bw[3], sizeof(h), cudaMemcpyDeviceToHost));
@@ -840,7 +1031,11 @@ __global__ void k_debug_count_batch(DScene S, long long n, const double* __restr
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     Ray r = mkray(vec(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]), vec(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]));
-    out[i] = debug_count_node(S, S.root, r, tmax[stride ? i : 0]);
+    ggen::QVM vm;
+    ggen::GCnt c;
+    ggen::gcnt_clear(c);
+    int ovf = 0;
+    out[i] = ggen::gq_debug_count(S, vm, S.root, r, tmax[stride ? i : 0], c, &ovf);
 }
 __global__ void k_debug_tint(DScene S, TileGeom g, DCamera cam, int tile_first, int tile_stride, double* __restrict__ out) {
     long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -850,7 +1045,11 @@ __global__ void k_debug_tint(DScene S, TileGeom g, DCamera cam, int tile_first, 
     if (ti % tile_stride != tile_first) return;
     Flt xc, yc;
     getCoordsf(g.width, g.height, (Flt)x, (Flt)y, xc, yc);
-    int dbg = debug_count_node(S, S.root, camera_ray(cam, xc, yc), GLM_INFINITY);
+    ggen::QVM vm;
+    ggen::GCnt c;
+    ggen::gcnt_clear(c);
+    int ovf = 0;
+    int dbg = ggen::gq_debug_count(S, vm, S.root, camera_ray(cam, xc, yc), GLM_INFINITY, c, &ovf);
     out[5 * pix] = ((Flt)(dbg % 30) / 60) + out[5 * pix];
     out[5 * pix + 1] = out[5 * pix + 1] + ((Flt)dbg / 1000);
 }
@@ -900,25 +1099,19 @@ extern "C" int glome_tile_rect(int width, int height, int blocksize, int i, int3
     return GLOME_OK;
 }
 
+static void trav_mark(GlomeScene* s, cudaStream_t st, int family);
+
 template <bool GEN, int MODE>
 static int launch_trace(GlomeScene* s, const TraceParams& P, cudaStream_t st) {
-    static int blocks_per_sm = 0;
     const int threads = GEN ? GEN_THREADS : 128;
-    if (!blocks_per_sm) {
-        int b = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace_samples<GEN, MODE>, threads, 0));
-        blocks_per_sm = b > 0 ? b : 1;
-    }
+    const int mi = MODE == 0 ? 0 : (MODE == 1 ? 1 : 2);
+    const int grid = GEN ? s->g_gen[mi] : s->g_flat[mi];
     CK(cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned int), st));
     TraceParams Q = P;
-    Q.chunk = 32;
-    if (GEN) {
-        const char* e = getenv("GLOME_GEN_CHUNK");
-        Q.chunk = e ? atoi(e) : 32;
-        if (Q.chunk < 1) Q.chunk = 1;
-        if (Q.chunk > 32) Q.chunk = 32;
-    }
-    k_trace_samples<GEN, MODE><<<s->sm_count * blocks_per_sm, threads, 0, st>>>(s->d, Q);
+    Q.chunk = GEN ? s->env_gen_chunk : 32;
+    if (GEN) trav_mark(s, st, 3);
+    k_trace_samples<GEN, MODE><<<grid, threads, 0, st>>>(s->d, Q);
+    if (GEN) trav_mark(s, st, 3);
     s->launches++;
     CK(cudaGetLastError());
     return GLOME_OK;
@@ -947,39 +1140,28 @@ static int wave_reserve(GlomeScene* s, size_t samples) {
     return GLOME_OK;
 }
 
-template <typename K>
-static int persistent_grid(GlomeScene* s, K kernel, int threads) {
-    int b = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, threads, 0) != cudaSuccess || b < 1) b = 1;
-    return s->sm_count * b;
-}
-
 static bool event_done(cudaEvent_t e) {
     if (cudaEventQuery(e) == cudaSuccess) return true;
     cudaGetLastError();  // cudaErrorNotReady is not an error here: do not leave it for the next CK()
     return false;
 }
-static void trav_mark(GlomeScene* s, cudaStream_t st) {
+static void trav_mark(GlomeScene* s, cudaStream_t st, int family) {
     if (!s->time_traversal) return;
     if (s->tev_used >= (int)s->tev.size()) {
         cudaEvent_t e;
         if (cudaEventCreate(&e) != cudaSuccess) return;
         s->tev.push_back(e);
+        s->tev_family.push_back(0);
     }
+    s->tev_family[s->tev_used] = family;
     cudaEventRecord(s->tev[s->tev_used++], st);
 }
 
 // One trace wave over the sample list described by W (mode / queue): K1 per segment, K2a, K1' per segment, K2b.
 static int launch_wave(GlomeScene* s, gwave::WaveParams W, long long max_samples, cudaStream_t st) {
     using namespace gwave;
-    static int g_bih[4] = {0, 0, 0, 0}, g_bvh = 0;
-    if (!g_bvh) {
-        g_bih[0] = persistent_grid(s, k_bih_traverse<false, false>, GW_THREADS);
-        g_bih[1] = persistent_grid(s, k_bih_traverse<false, true>, GW_THREADS);
-        g_bih[2] = persistent_grid(s, k_bih_traverse<true, false>, GW_THREADS);
-        g_bih[3] = persistent_grid(s, k_bih_traverse<true, true>, GW_THREADS);
-        g_bvh = persistent_grid(s, k_bvh_closest, 128);
-    }
+    const int* g_bih = s->g_bih;
+    const int g_bvh = s->g_bvh;
     long long blocks = (max_samples + 127) / 128;
     long long cap = (long long)s->sm_count * 16;
     int sgrid = (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
@@ -992,15 +1174,15 @@ static int launch_wave(GlomeScene* s, gwave::WaveParams W, long long max_samples
         if (sg.kind == SEG_BIH) {
             bool linear = (s->segs_linear[i] != 0);
             unsigned int* ctr = s->w_counters + (s->w_counter_next++ & 1023);
-            trav_mark(s, st);
+            trav_mark(s, st, 0);
             if (linear) k_bih_traverse<false, true><<<g_bih[1], GW_THREADS, 0, st>>>(s->d, W, (int)i, sg, ctr);
             else k_bih_traverse<false, false><<<g_bih[0], GW_THREADS, 0, st>>>(s->d, W, (int)i, sg, ctr);
-            trav_mark(s, st);
+            trav_mark(s, st, 0);
         } else if (sg.kind == SEG_MESH) {
             unsigned int* ctr = s->w_counters + (s->w_counter_next++ & 1023);
-            trav_mark(s, st);
+            trav_mark(s, st, 2);
             k_bvh_closest<<<g_bvh, 128, 0, st>>>(s->d, W, (int)i, sg, ctr);
-            trav_mark(s, st);
+            trav_mark(s, st, 2);
         } else {
             k_prims_closest<<<sgrid, 128, 0, st>>>(s->d, W, (int)i, sg);
         }
@@ -1016,10 +1198,10 @@ static int launch_wave(GlomeScene* s, gwave::WaveParams W, long long max_samples
             if (sg.kind == SEG_BIH) {
                 bool linear = (s->segs_linear[i] != 0);
                 unsigned int* ctr = s->w_counters + (s->w_counter_next++ & 1023);
-                trav_mark(s, st);
+                trav_mark(s, st, 1);
                 if (linear) k_bih_traverse<true, true><<<g_bih[3], GW_THREADS, 0, st>>>(s->d, W, (int)i, sg, ctr);
                 else k_bih_traverse<true, false><<<g_bih[2], GW_THREADS, 0, st>>>(s->d, W, (int)i, sg, ctr);
-                trav_mark(s, st);
+                trav_mark(s, st, 1);
             } else if (sg.kind == SEG_PRIMS) {
                 k_prims_any<<<sgrid, 128, 0, st>>>(s->d, W, sg);
             } else continue;  // a Mesh casts no shadows (Mesh.hs:210)
@@ -1040,6 +1222,10 @@ extern "C" int glome_render_dev(GlomeScene* s, const GlomeCamera* cam, int width
     if (o->debug_heatmap && (o->mode != GLOME_MODE_ONE_RAY || o->tint_depth)) {
         g_err = "debug_heatmap is get_color_debug per pixel (Glome.hs:57-60): GLOME_MODE_ONE_RAY without tint_depth only";
         return GLOME_EINVAL;
+    }
+    if (s->scene_class == GLOME_CLASS_GENERAL && o->recurs > GS_MAX_RECURS) {
+        g_err = "recurs above the general tracer's limit of " + std::to_string(GS_MAX_RECURS) + " generations";
+        return GLOME_ELIMIT;
     }
     CK(cudaSetDevice(s->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -1091,10 +1277,10 @@ extern "C" int glome_render_dev(GlomeScene* s, const GlomeCamera* cam, int width
             }
         } else {
             // workspace: v (pass 1-4 samples), ray queue
-            if (s->ws_pix < npix) {
-                cudaFree(s->v); s->v = nullptr; s->ws_pix = 0;
+            if (s->v_pix < npix) {
+                cudaFree(s->v); s->v = nullptr; s->v_pix = 0;
                 CK(cudaMalloc((void**)&s->v, npix * 5 * sizeof(double)));
-                s->ws_pix = npix;
+                s->v_pix = npix;
             }
             if (s->queue_cap < npix) {
                 cudaFree(s->queue); s->queue = nullptr; s->queue_cap = 0;
@@ -1110,15 +1296,14 @@ extern "C" int glome_render_dev(GlomeScene* s, const GlomeCamera* cam, int width
             // interpreter is latency-bound per warp), so passes 1-4 are speculated: every pixel centre is traced
             // once, up front, and the per-pass decisions copy from that buffer.  get_color is a pure function of the
             // sample position, so the frame is bit-identical to the adaptive schedule; only the ray count differs.
-            bool speculate = !s->use_wave && !getenv("GLOME_NO_SPECULATE");
+            bool speculate = !s->use_wave && !s->env_no_speculate;
             if (s->use_wave) {
                 // Flat scenes: a wave is cheap per ray but five dependent waves are not (each sits on its latency
                 // floor), so the same speculation pays when the adaptive schedule ends up tracing most pixel centres
                 // anyway (a cloud of small spheres: 95 %) and costs rays when it does not (a smooth mesh: 30 %).
                 // The schedule of this frame follows what the previous frame of the same geometry did; the frame
                 // itself is bit-identical either way.
-                const char* e = getenv("GLOME_AA_SPECULATE");
-                if (e) speculate = atoi(e) != 0;
+                if (s->env_aa_speculate >= 0) speculate = s->env_aa_speculate != 0;
                 else if (s->aa_valid && s->aa_w == width && s->aa_h == height && s->aa_first == o->tile_first &&
                          s->aa_stride == o->tile_stride && s->aa_bs == o->blocksize && event_done(s->aa_ev)) {
                     long long centres = 0, traced = 0;
@@ -1189,7 +1374,11 @@ extern "C" int glome_render_dev(GlomeScene* s, const GlomeCamera* cam, int width
         double tms = 0;
         for (int k = 0; k + 1 < s->tev_used; k += 2) {
             float t = 0;
-            if (cudaEventElapsedTime(&t, s->tev[k], s->tev[k + 1]) == cudaSuccess) tms += t;
+            if (cudaEventElapsedTime(&t, s->tev[k], s->tev[k + 1]) == cudaSuccess) {
+                tms += t;
+                stats->family_ms[s->tev_family[k] & 3] += t;
+                stats->family_launches[s->tev_family[k] & 3] += 1;
+            }
         }
         stats->traverse_ms = tms;
         stats->traverse_launches = s->tev_used / 2;
@@ -1202,13 +1391,15 @@ extern "C" int glome_render(GlomeScene* s, const GlomeCamera* cam, int width, in
     if (!s || (!tcolor && !rgb8) || width <= 0 || height <= 0) { g_err = "bad argument"; return GLOME_EINVAL; }
     CK(cudaSetDevice(s->device));
     size_t npix = (size_t)width * height;
-    if (!s->v2 || s->ws_pix < npix) {
-        cudaFree(s->v2); cudaFree(s->rgb8); cudaFree(s->v);
-        s->v2 = nullptr; s->rgb8 = nullptr; s->v = nullptr; s->ws_pix = 0;
+    if (s->v2_pix < npix) {
+        cudaFree(s->v2); s->v2 = nullptr; s->v2_pix = 0;
         CK(cudaMalloc((void**)&s->v2, npix * 5 * sizeof(double)));
+        s->v2_pix = npix;
+    }
+    if (rgb8 && s->rgb8_pix < npix) {
+        cudaFree(s->rgb8); s->rgb8 = nullptr; s->rgb8_pix = 0;
         CK(cudaMalloc((void**)&s->rgb8, npix * sizeof(uint32_t)));
-        CK(cudaMalloc((void**)&s->v, npix * 5 * sizeof(double)));
-        s->ws_pix = npix;
+        s->rgb8_pix = npix;
     }
     // pixels of unselected tiles must be left untouched: start from the caller's buffer
     if (o && o->tile_stride > 1) {

@@ -844,9 +844,8 @@ __global__ void __launch_bounds__(128) k_shade(DScene S, WaveParams P, const Seg
         if (ri.flags) n_ovf++;
         ColorA colora = mkca(0, 0, 0, 0);
         if (ri.hit && P.recurs != 0) {
-            LightCtx ctx;
-            ctx.done = 0; ctx.n = 0;
-            RayCounters rc = {0, 0, 0, {0, 0, 0, 0}};
+            LightSel ctx;
+            ctx.done = 0; ctx.first = lfirst; ctx.count = lcnt; ctx.mask = 0;
             Vec eyedir = vinvert(ray.d);
             for (int i = 0; i < ri.tex.n; i++) {
                 if (colora.a + GLM_DELTA >= 1) continue;  // opaque (Trace.hs:50)
@@ -857,30 +856,15 @@ __global__ void __launch_bounds__(128) k_shade(DScene S, WaveParams P, const Seg
                         Ray sr; Flt d, llen; Vec ldir; bool ns;
                         if (!light_ray(S, P.surf + 6 * s, lfirst + li, sr, d, ldir, llen, ns)) continue;
                         if (ns && ((oc >> (lfirst + li)) & 1u)) continue;
-                        const GlomeLight* Lp = S.lights + lfirst + li;
-                        Flt fall = 1 / (llen * llen);
-                        if (ctx.n < GDEV_MAX_LIGHTS) {
-                            ctx.col[ctx.n].r = Lp->color[0] * fall;
-                            ctx.col[ctx.n].g = Lp->color[1] * fall;
-                            ctx.col[ctx.n].b = Lp->color[2] * fall;
-                            ctx.dir[ctx.n] = ldir;
-                            ctx.n++;
-                        }
+                        ctx.mask |= 1ull << li;
                     }
                 }
                 MatVal m;
-                eval_texture(S, ri.tex.v[i], ri, m, rc);
+                eval_texture(S, ri.tex.v[i], ri.pos, m, n_perlin);
                 ColorA colorb;
-                if (m.kind == GLOME_MAT_SURFACE) shade_surface(ctx, m.p, ri.norm, eyedir, colorb);
-                else if (m.kind == GLOME_MAT_BLEND) {
-                    ColorA ca, cb;
-                    shade_surface(ctx, S.materials[m.a].p, ri.norm, eyedir, ca);
-                    shade_surface(ctx, S.materials[m.b].p, ri.norm, eyedir, cb);
-                    colorb = caweight(ca, cb, m.p[0]);
-                } else colorb = mkca(0, 0, 0, 0);
+                mshade_flat(S, ctx, m, ri, eyedir, colorb);
                 colora = cafold(colora, colorb);
             }
-            n_perlin += rc.perlin_range;
         }
         TCw col;
         col.r = colora.r; col.g = colora.g; col.b = colora.b; col.a = colora.a;

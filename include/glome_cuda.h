@@ -240,6 +240,12 @@ typedef struct GlomeRenderStats {
     int64_t tests_tri;      /* mesh triangles tested (32 B Tri + 72 B vertices)       */
     double traverse_ms;     /* device time of the traversal kernels alone (K1 + K1'), CUDA events   */
     int64_t traverse_launches;
+    /* the same, per kernel family: [0] k_bih_traverse<closest>  [1] k_bih_traverse<any>  [2] k_bvh_closest
+     * [3] k_gen_trace (the general-scene tracer: traversal and shading in one persistent kernel) */
+    double family_ms[4];
+    int64_t family_launches[4];
+    int64_t visits_instance; /* Instance transforms applied (192 B Xfm each); general scenes          */
+    int64_t csg_steps;       /* rayint_advance re-issues (Solid.hs:85-91); general scenes             */
 } GlomeRenderStats;
 
 typedef struct GlomeScene GlomeScene; /* opaque device-resident scene */
