@@ -315,12 +315,11 @@ struct TraceParams {
     DevStats* st;
 };
 
-template <bool GEN, int MODE>
-__global__ void __launch_bounds__(GEN ? GEN_THREADS : 128, GEN ? GEN_MINBLOCKS : 1) k_trace_samples(DScene S, TraceParams P) {
+// flat-class scenes the wavefront pipeline cannot take (more than 32 lights, more than GW_MAX_SEGS segments): one thread per sample
+template <int MODE>
+__global__ void __launch_bounds__(128, 1) k_trace_samples(DScene S, TraceParams P) {
     const int lane = threadIdx.x & 31;
     RayCounters rc = {0, 0, 0, {0, 0, 0, 0}};
-    ggen::GCnt gc;
-    ggen::gcnt_clear(gc);
     unsigned int ovf = 0, nprim = 0;
     const long long total = (MODE == 0) ? (long long)P.n_sel * P.g.slots_per_tile : (long long)(*P.queue_count);
     // Rays per warp-chunk.  The general interpreter serialises divergent lanes, so when a wave has too few samples
@@ -355,13 +354,7 @@ __global__ void __launch_bounds__(GEN ? GEN_THREADS : 128, GEN ? GEN_MINBLOCKS :
             else getCoordsf(P.g.width, P.g.height, (Flt)x, (Flt)y, xc, yc);
             ColorA c;
             Flt hd;
-            if constexpr (GEN) {
-                ggen::SHM sh;
-                int fl = 0;
-                ggen::gs_trace<false>(S, sh, 0, S.root, camera_ray(P.cam, xc, yc), GLM_INFINITY, P.recurs, c, gc, fl, nullptr);
-                hd = ggen::ghit_depth(sh.tf[0].ri);
-                if (fl) ovf++;
-            } else {
+            {
                 Hit h;
                 trace_flat(S, 0, S.root, camera_ray(P.cam, xc, yc), GLM_INFINITY, P.recurs, c, h, rc);
                 hd = ridepth(h);
@@ -387,9 +380,104 @@ __global__ void __launch_bounds__(GEN ? GEN_THREADS : 128, GEN ? GEN_MINBLOCKS :
         }
     }
     __syncwarp();
-    if constexpr (GEN) flush_gcnt(P.st, nprim, gc, ovf);
-    else flush_counters(P.st, nprim, rc, ovf);
+    flush_counters(P.st, nprim, rc, ovf);
 }
+
+// ---------------------------------------------------------------------------------------------
+// General scenes: the persistent tracer.  A warp takes an 8x4 micro-tile of samples; every lane runs the scene-graph
+// machine of glome_gen.cuh (QVM for rayint / shadow, SHM for trace + materialShader) on its sample.  Stacks (control
+// words, hit slots, trace / material frames) are the thread's local memory: no device recursion.
+// Measured on B200 (config 1 / config 4, ms per frame): a lane that pulls a new sample as soon as its own is done
+// (per-lane refill, as the flat kernels do) is 2.7x SLOWER here (41 / 28 vs 15 / 8.4): the machine's rounds cost the sum
+// of the states present in the warp, and coherent neighbours stay in the same state while strangers do not.
+// ---------------------------------------------------------------------------------------------
+#ifndef GEN_SYNC_ROUNDS
+#define GEN_SYNC_ROUNDS 1  /* 1: the lanes of a warp start their queries together (warp-synchronous rounds) */
+#endif
+template <int MODE>
+__global__ void __launch_bounds__(GEN_THREADS, GEN_MINBLOCKS) k_gen_trace(DScene S, TraceParams P) {
+    const unsigned int FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    ggen::SHM sh;
+    ggen::QRegs q;
+    ggen::SRegs sr;
+    ggen::GCnt gc;
+    ggen::gcnt_clear(gc);
+    unsigned int ovf = 0, nprim = 0;
+    const long long total = (MODE == 0) ? (long long)P.n_sel * P.g.slots_per_tile : (long long)(*P.queue_count);
+    const unsigned int chunk = (unsigned int)P.chunk;
+    q.st = ggen::GS_DONE;
+    for (;;) {
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(P.work_counter, chunk);
+        base = __shfl_sync(FULL, base, 0);
+        if ((long long)base >= total) break;
+        const long long w = (long long)base + lane;
+        bool valid = w < total && lane < (int)chunk;
+        int px = 0, py = 0;
+        if (MODE == 0) {
+            if (valid) {
+                int k = (int)(w / P.g.slots_per_tile), local = (int)(w % P.g.slots_per_tile);
+                int ti = P.tile_first + k * P.tile_stride;
+                int xt, yt, tw, th;
+                tile_rect(P.g, ti, xt, yt, tw, th);
+                int blk = local >> 5, l = local & 31;
+                int qx = (blk % P.g.nbx) * 8 + (l & 7), qy = (blk / P.g.nbx) * 4 + (l >> 3);
+                valid = qx < tw && qy < th;
+                px = xt + qx; py = yt + qy;
+            }
+        } else if (valid) {
+            int pix = P.queue[w];
+            px = pix % P.g.width; py = pix / P.g.width;
+        }
+        sr.st = ggen::SS_FINISHED;
+        if (valid) {
+            Flt xc, yc;
+            if (MODE == 5) getCoordsf(P.g.width, P.g.height, (Flt)px + 0.5, (Flt)py + 0.5, xc, yc);
+            else getCoordsf(P.g.width, P.g.height, (Flt)px, (Flt)py, xc, yc);
+            ggen::shm_start(sr, sh, 0, S.root, camera_ray(P.cam, xc, yc), GLM_INFINITY, P.recurs, nullptr);
+        }
+        // rounds: every unfinished lane advances its shading machine to its next query (or to the end of the sample), then
+        // all those queries run side by side from their first step: the shadow rays of neighbouring pixels towards one
+        // light, or their reflected rays, walk the scene graph as coherently as the primary rays did
+        for (;;) {
+            bool need = false;
+            if (sr.st != ggen::SS_FINISHED) need = ggen::shm_step<false>(S, sr, sh, q, gc, nullptr);
+#if GEN_SYNC_ROUNDS
+            if (__ballot_sync(FULL, need) == 0) break;
+            while (__ballot_sync(FULL, need && q.st != ggen::GS_DONE)) {
+                if (need && q.st != ggen::GS_DONE) ggen::qvm_step(S, q, sh.q, gc);
+            }
+#else
+            if (!need) break;
+            while (q.st != ggen::GS_DONE) ggen::qvm_step(S, q, sh.q, gc);
+#endif
+        }
+        if (valid) {  // get_color's result for this sample
+            nprim++;
+            if (sr.fl) ovf++;
+            TC col;
+            col.r = sr.rv_c.r; col.g = sr.rv_c.g; col.b = sr.rv_c.b; col.a = sr.rv_c.a; col.d = ggen::ghit_depth(sh.tf[0].ri);
+            const size_t pix = (size_t)py * P.g.width + px;
+            if (MODE == 0) {
+                if (P.tint) col.r = col.r + (col.d / 400);  // Glome.hs:174
+                st_tc(P.out, pix, col);
+            } else if (MODE == 1) {
+                st_tc(P.out, pix, col);
+            } else {
+                int tx = px / P.g.bs, ty = py / P.g.bs;
+                int xt = tx * P.g.bs, yt = ty * P.g.bs;
+                int tw = min(P.g.bs, P.g.width - xt), th = min(P.g.bs, P.g.height - yt);
+                TC a = getc(P.v, P.g.width, xt, yt, tw, th, px, py), b = getc(P.v, P.g.width, xt, yt, tw, th, px, py + 1);
+                TC cc = getc(P.v, P.g.width, xt, yt, tw, th, px + 1, py + 1), d = getc(P.v, P.g.width, xt, yt, tw, th, px + 1, py);
+                st_tc(P.out, pix, pass5_combine(col, a, b, cc, d, px == xt + tw - 1, py == yt + th - 1));
+            }
+        }
+    }
+    __syncwarp();
+    flush_gcnt(P.st, nprim, gc, ovf);
+}
+
 
 // ---------------------------------------------------------------------------------------------
 // K3: adaptive-AA decide kernels (Glome.hs:226-323).  One block per selected tile.  Each
@@ -785,6 +873,11 @@ static int scene_create_impl(GlomeScene* s, const GlomeFlatScene* desc, int devi
         if ((rc = upload(s, nodes.data(), nodes.size(), &s->d.nodes))) return rc;
         if ((rc = upload(s, ipool.data(), ipool.size(), &s->d.ipool))) return rc;
         if ((rc = upload(s, tagvals.data(), tagvals.size(), &s->d.tagvals))) return rc;
+        std::vector<int32_t> items;
+        glome_tagmap::build_items(nodes, items);
+        const int32_t* items_dev = nullptr;
+        if ((rc = upload(s, items.data(), items.size(), &items_dev))) return rc;
+        s->d.items = reinterpret_cast<const int4*>(items_dev);
     } else {
         if ((rc = upload(s, desc->nodes, (size_t)desc->n_nodes, &s->d.nodes))) return rc;
         if ((rc = upload(s, desc->ipool, (size_t)desc->n_ipool, &s->d.ipool))) return rc;
@@ -814,12 +907,12 @@ static int scene_create_impl(GlomeScene* s, const GlomeFlatScene* desc, int devi
     s->g_bih[2] = persistent_grid(s, gwave::k_bih_traverse<true, false>, GW_THREADS);
     s->g_bih[3] = persistent_grid(s, gwave::k_bih_traverse<true, true>, GW_THREADS);
     s->g_bvh = persistent_grid(s, gwave::k_bvh_closest, 128);
-    s->g_gen[0] = persistent_grid(s, k_trace_samples<true, 0>, GEN_THREADS);
-    s->g_gen[1] = persistent_grid(s, k_trace_samples<true, 1>, GEN_THREADS);
-    s->g_gen[2] = persistent_grid(s, k_trace_samples<true, 5>, GEN_THREADS);
-    s->g_flat[0] = persistent_grid(s, k_trace_samples<false, 0>, 128);
-    s->g_flat[1] = persistent_grid(s, k_trace_samples<false, 1>, 128);
-    s->g_flat[2] = persistent_grid(s, k_trace_samples<false, 5>, 128);
+    s->g_gen[0] = persistent_grid(s, k_gen_trace<0>, GEN_THREADS);
+    s->g_gen[1] = persistent_grid(s, k_gen_trace<1>, GEN_THREADS);
+    s->g_gen[2] = persistent_grid(s, k_gen_trace<5>, GEN_THREADS);
+    s->g_flat[0] = persistent_grid(s, k_trace_samples<0>, 128);
+    s->g_flat[1] = persistent_grid(s, k_trace_samples<1>, 128);
+    s->g_flat[2] = persistent_grid(s, k_trace_samples<5>, 128);
     if (s->scene_class == GLOME_CLASS_FLAT && !getenv("GLOME_FLAT_MEGAKERNEL") && build_segments(desc, s->segs) &&
         ls[0] + ls[1] <= 32) {
         CK(cudaMalloc((void**)&s->segs_dev, sizeof(gwave::Seg) * s->segs.size()));
@@ -975,7 +1068,7 @@ extern "C" int glome_trace_batch(GlomeScene* s, int64_t n, const double* rays, c
         k_trace_batch<false><<<grid, 128>>>(s->d, n, (const double*)s->bw[0], (const double*)s->bw[1], tmax_stride, recurs, d_rgba,
                                             d_depth, hits ? (GlomeHit*)s->bw[3] : nullptr, s->stats);
     else
-        k_trace_batch<true><<<grid, 128>>>(s->d, n, (const double*)s->bw[0], (const double*)s->bw[1], tmax_stride, recurs, d_rgba,
+        k_trace_batch<true><<<2 * grid, 64>>>(s->d, n, (const double*)s->bw[0], (const double*)s->bw[1], tmax_stride, recurs, d_rgba,
                                            d_depth, hits ? (GlomeHit*)s->bw[3] : nullptr, s->stats);
     s->launches++;
     CK(cudaGetLastError());
@@ -1009,9 +1102,9 @@ extern "C" int glome_get_tags(GlomeScene* s, const GlomeCamera* cam, int width, 
     CK(cudaMemcpy(s->bw[0], ray, 48, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(s->bw[1], &tmax, 8, cudaMemcpyHostToDevice));
     if (s->scene_class == GLOME_CLASS_FLAT)
-        k_trace_tags<false><<<1, 128>>>(s->d, 1, (const double*)s->bw[0], (const double*)s->bw[1], 0, recurs, (GlomeHit*)s->bw[3], (int*)s->bw[2]);
+        k_trace_tags<false><<<1, 64>>>(s->d, 1, (const double*)s->bw[0], (const double*)s->bw[1], 0, recurs, (GlomeHit*)s->bw[3], (int*)s->bw[2]);
     else
-        k_trace_tags<true><<<1, 128>>>(s->d, 1, (const double*)s->bw[0], (const double*)s->bw[1], 0, recurs, (GlomeHit*)s->bw[3], (int*)s->bw[2]);
+        k_trace_tags<true><<<1, 64>>>(s->d, 1, (const double*)s->bw[0], (const double*)s->bw[1], 0, recurs, (GlomeHit*)s->bw[3], (int*)s->bw[2]);
     s->launches++;
     CK(cudaGetLastError());
     int out[2 + 16];
@@ -1109,9 +1202,11 @@ static int launch_trace(GlomeScene* s, const TraceParams& P, cudaStream_t st) {
     CK(cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned int), st));
     TraceParams Q = P;
     Q.chunk = GEN ? s->env_gen_chunk : 32;
-    if (GEN) trav_mark(s, st, 3);
-    k_trace_samples<GEN, MODE><<<grid, threads, 0, st>>>(s->d, Q);
-    if (GEN) trav_mark(s, st, 3);
+    if (GEN) {
+        trav_mark(s, st, 3);
+        k_gen_trace<MODE><<<grid, threads, 0, st>>>(s->d, Q);
+        trav_mark(s, st, 3);
+    } else k_trace_samples<MODE><<<grid, threads, 0, st>>>(s->d, Q);
     s->launches++;
     CK(cudaGetLastError());
     return GLOME_OK;

@@ -55,6 +55,7 @@ struct DScene {
     const GlomeLight* __restrict__ lights;
     const int32_t* __restrict__ lightsets;
     const int32_t* __restrict__ tagvals;  // general-class scenes: dense tag id -> the caller's tag value (glome_gen.cuh)
+    const int4* __restrict__ items;       // general-class scenes: one item descriptor per node (glome_tagmap.h)
     int root;
     int n_lights;
 };
@@ -252,6 +253,54 @@ GD_FN bool prim_box(const double* __restrict__ p, const Ray& r, Flt d, Flt& t, V
             pos = vscaleadd(r.o, r.d, lastin);
         }
     }
+    return true;
+}
+// the same, with 1/d handed in: the three quotients depend on the ray only, so a caller testing many boxes with one ray
+// (a group of boxes, a BIH) computes them once.  Bit-identical to prim_box.
+template <bool FULL>
+GD_FN bool prim_box_rcp(const double* __restrict__ p, const Ray& r, Flt dxrcp, Flt dyrcp, Flt dzrcp, Flt d, Flt& t, Vec& pos, Vec& n) {
+    Bbox b = ldbb(p);
+    Flt dx = r.d.x, dy = r.d.y, dz = r.d.z;
+    Flt inx, outx, iny, outy, inz, outz;
+    slab(dx > 0, b.p1.x, b.p2.x, r.o.x, dxrcp, inx, outx);
+    slab(dy > 0, b.p1.y, b.p2.y, r.o.y, dyrcp, iny, outy);
+    slab(dz > 0, b.p1.z, b.p2.z, r.o.z, dzrcp, inz, outz);
+    Flt lastin = fmax3(inx, iny, inz);
+    Flt firstout = fmin3(outx, outy, outz);
+    if (lastin > firstout || firstout < 0 || lastin > d) return false;
+    if (lastin < 0) {  // origin is inside
+        t = firstout;
+        if (FULL) {
+            if (outx == firstout) n = (dx > 0) ? vec(1, 0, 0) : vec(-1, 0, 0);
+            else if (outy == firstout) n = (dy > 0) ? vec(0, 1, 0) : vec(0, -1, 0);
+            else n = (dz > 0) ? vec(0, 0, 1) : vec(0, 0, -1);
+            pos = vscaleadd(r.o, r.d, firstout);
+        }
+    } else {
+        t = lastin;
+        if (FULL) {
+            if (inx == lastin) n = (dx > 0) ? vec(-1, 0, 0) : vec(1, 0, 0);
+            else if (iny == lastin) n = (dy > 0) ? vec(0, -1, 0) : vec(0, 1, 0);
+            else n = (dz > 0) ? vec(0, 0, -1) : vec(0, 0, 1);
+            pos = vscaleadd(r.o, r.d, lastin);
+        }
+    }
+    return true;
+}
+// bbclip_ub (Vec.hs:743-762) with 1/d handed in
+GD_FN void bbclip_ub_pre(const Ray& r, Flt dxrcp, Flt dyrcp, Flt dzrcp, const Bbox& b, Flt& near_, Flt& far_) {
+    Flt inx, outx, iny, outy, inz, outz;
+    slab(r.d.x > 0, b.p1.x, b.p2.x, r.o.x, dxrcp, inx, outx);
+    slab(r.d.y > 0, b.p1.y, b.p2.y, r.o.y, dyrcp, iny, outy);
+    slab(r.d.z > 0, b.p1.z, b.p2.z, r.o.z, dzrcp, inz, outz);
+    near_ = fmax3(inx, iny, inz);
+    far_ = fmin3(outx, outy, outz);
+}
+GD_FN bool shadow_box_rcp(const double* __restrict__ p, const Ray& r, Flt dxrcp, Flt dyrcp, Flt dzrcp, Flt d) {  // Box.hs:56-62
+    Bbox b = ldbb(p);
+    Flt near_, far_;
+    bbclip_ub_pre(r, dxrcp, dyrcp, dzrcp, b, near_, far_);
+    if ((near_ > far_) || far_ <= 0 || far_ > d) return false;
     return true;
 }
 GD_FN bool shadow_box(const double* __restrict__ p, const Ray& r, Flt d) {  // Box.hs:56-62

@@ -329,7 +329,7 @@ enum {
     GF_BIH,         // bottom of a BIH's TRAV entries                           [hdr(previous BIH node)]
     GF_LIST,        // resume a list after a complex item                       [d ld hdr(next, end)]
     GF_CTX,         // restore the texture / tag context                        [tex.lo tex.hi tag.lo tag.hi hdr]
-    GF_INST,        // Instance (Solid.hs:386-403, 464-471)                     [o.xyz d.xyz d invlenscale hdr(node, parent slot)]
+    GF_INST,        // Instance (Solid.hs:386-403, 464-471)                     [o.xyz d.xyz d invlenscale 1/d.xyz hdr(node, parent slot)]
     GF_MODE,        // a rayint stood in for a shadow (Solid.hs:218-221)        [hdr(slot, previous acc)]
     GF_GATE,        // Bound (Bound.hs:30-49): shadow of the bounding object    [hdr(bounded node, previous mode)]
     GF_OR,          // InnerBound shadow (Bound.hs:101-103)                     [hdr(second node)]
@@ -371,37 +371,175 @@ GD_FN Flt gq_w2d(unsigned long long w) {
 
 enum { GS_ENTER = 0, GS_BRANCH, GS_LIST, GS_RET, GS_DONE };
 
-// Evaluate one query to completion.
-//   shadow_q = false: rayint root ray d [] []  -> result in vm.slot[0]; returns its hit flag
-//   shadow_q = true : shadow root ray d        -> return value
-GD_NOINLINE bool gq_query(const DScene& S, QVM& vm, int root, const Ray& qray, Flt qd, bool shadow_q, GCnt& cnt) {
+// item descriptor classes / flags (glome_tagmap.h: build_items)
+enum { GI_DEAD = 0, GI_PRIM = 1, GI_INST_PRIM = 2, GI_COMPLEX = 3 };
+#define GI_VIS_R 0x100
+#define GI_VIS_S 0x200
+#define GI_WRAPPED 0x400
+
+// the primitive tests of the machine: rayint with position + normal, and shadow.  (rx, ry, rz) = 1 / ray.d, computed
+// once per ray by the caller (only the box uses it).
+GD_FN bool gq_prim_rayint(const DScene& S, int type, int payload, const Ray& r, Flt rx, Flt ry, Flt rz, Flt d, Flt& t, Vec& pos,
+                          Vec& n) {
+    const double* p = S.dpool + payload;
+    switch (type) {
+        case GLOME_SPHERE: return prim_sphere<true>(p, r, d, t, pos, n);
+        case GLOME_TRIANGLE: {
+            Vec z = vec(0, 0, 0);
+            return prim_triangle<true>(ldv(p), ldv(p + 3), ldv(p + 6), false, z, z, z, r, d, t, pos, n);
+        }
+        case GLOME_TRIANGLENORM:
+            return prim_triangle<true>(ldv(p), ldv(p + 3), ldv(p + 6), true, ldv(p + 9), ldv(p + 12), ldv(p + 15), r, d, t, pos, n);
+        case GLOME_BOX: return prim_box_rcp<true>(p, r, rx, ry, rz, d, t, pos, n);
+        case GLOME_PLANE: return prim_plane<true>(p, r, d, t, pos, n);
+        case GLOME_DISC: return prim_disc_v<true>(ldv(p), ldv(p + 3), p[6], r, d, t, pos, n);
+        case GLOME_CYLINDER: return prim_cylinder<true>(p, r, d, t, pos, n);
+        case GLOME_CONE: return prim_cone<true>(p, r, d, t, pos, n);
+    }
+    return false;
+}
+// the primitives with a shadow method of their own (Sphere.hs:51-71, Triangle.hs:82-107, Box.hs:56-62); the others fall
+// back on rayint's hit flag (Solid.hs:218-221; shadow_cone, Cone.hs:206-245, is rayint_cone's hit test)
+GD_FN bool gq_has_shadow_method(int type) { return type <= GLOME_BOX; }
+GD_FN bool gq_prim_shadow(const DScene& S, int type, int payload, const Ray& r, Flt rx, Flt ry, Flt rz, Flt d) {
+    const double* p = S.dpool + payload;
+    switch (type) {
+        case GLOME_SPHERE: return shadow_sphere(p, r, d);
+        case GLOME_TRIANGLE:
+        case GLOME_TRIANGLENORM: return shadow_triangle(ldv(p), ldv(p + 3), ldv(p + 6), r, d);
+        case GLOME_BOX: return shadow_box_rcp(p, r, rx, ry, rz, d);
+    }
+    return false;
+}
+
+#define GI_HAS_META 0x800 /* a Tex or Tag somewhere below: get_metainfo can return something */
+
+// A primitive hit as the test produces it: world-space depth / position / normal, and the ray it was tested with
+struct SimpleHit { Flt t; Vec pos, norm; Ray ray; };
+
+// rayint / shadow of a simple item -- `{Tex,Tag}* prim` or `{..}* Instance ({..}* prim)` (Solid.hs:388-403) -- described by
+// its item record.  The ONE copy of the primitive tests in a kernel: the list loop and the CSG evaluators all call it.
+// (rx, ry, rz) = 1 / r.d of the caller's ray.  smode: only the hit flag is wanted (shadow).
+GD_NOINLINE bool gq_test_simple(const DScene& S, int4 it, Flt ox, Flt oy, Flt oz, Flt dx, Flt dy, Flt dz, Flt rx, Flt ry, Flt rz, Flt d,
+                                bool smode, SimpleHit* out, GCnt* cnt) {
+    const int cls = it.x & 15, ptype = (it.x >> 4) & 15;
+    Ray tr = mkray(vec(ox, oy, oz), vec(dx, dy, dz));
+    Flt td = d, invls = 1;
+    const Flt* xfm = nullptr;
+    if (cls == GI_INST_PRIM) {
+        cnt->inst++;
+        xfm = S.dpool + it.w;
+        const Vec newdir = invxfm_vec(xfm, tr.d);
+        const Vec neworig = invxfm_point(xfm, tr.o);
+        const Flt lenscale = vlen(newdir);
+        invls = 1 / lenscale;
+        tr = mkray(neworig, vscale(newdir, invls));
+        td = d * lenscale;
+        if (ptype == GLOME_BOX) { rx = 1 / tr.d.x; ry = 1 / tr.d.y; rz = 1 / tr.d.z; }
+    }
+    cnt->prim++;
+    if (smode && gq_has_shadow_method(ptype)) return gq_prim_shadow(S, ptype, it.z, tr, rx, ry, rz, td);
+    Flt t; Vec pos, n;
+    if (!gq_prim_rayint(S, ptype, it.z, tr, rx, ry, rz, td, t, pos, n)) return false;
+    if (smode) return true;
+    out->ray = tr;
+    if (xfm) { out->t = t * invls; out->pos = xfm_point(xfm, pos); out->norm = vnorm(invxfm_norm(xfm, n)); }
+    else { out->t = t; out->pos = pos; out->norm = n; }
+    return true;
+}
+
+// record a simple item's hit: the context stacks plus the item's own wrappers, outermost first (Tex.hs:54,66)
+GD_FN void gq_fill_hit(const DScene& S, GHit& a, const int4& it, int item, const SimpleHit& h, const PStk& ctex, const PStk& ctag,
+                       int& mflags) {
+    a.hit = 1; a.t = h.t; a.pos = h.pos; a.norm = h.norm; a.ray = h.ray; a.prim = it.y; a.sub = -1;
+    PStk wtx = ctex, wtg = ctag;
+    if (it.x & GI_WRAPPED) {
+        int wj = item;
+        GlomeNode w = S.nodes[wj];
+        for (;;) {
+            if (w.type == GLOME_TEX) { if (pstk_cons(wtx, w.b)) mflags |= GLOME_HITFLAG_STACK_OVERFLOW; }
+            else if (w.type == GLOME_TAG) { if (pstk_cons(wtg, w.b)) mflags |= GLOME_HITFLAG_STACK_OVERFLOW; }
+            else if (w.type == GLOME_NOSHADOW || w.type == GLOME_INSTANCE) {}
+            else break;
+            wj = w.a; w = S.nodes[wj];
+        }
+    }
+    a.tex = wtx; a.tag = wtg;
+}
+
+// inside s pt with the item record's short cuts
+GD_FN bool gq_inside_fast(const DScene& S, int node, const Vec& pt, int* ovf) {
+    const int4 it = gd_ldg(S.items + node);
+    const int cls = it.x & 15;
+    if (cls == GI_PRIM || cls == GI_INST_PRIM) {
+        GlomeNode pn;
+        pn.type = (it.x >> 4) & 15; pn.a = it.z; pn.b = 0; pn.c = 0;
+        return prim_inside(S, pn, cls == GI_PRIM ? pt : invxfm_point(S.dpool + it.w, pt));
+    }
+    if (cls == GI_DEAD) return false;
+    return gq_inside(S, node, pt, ovf);
+}
+GD_FN bool gq_inside_all_fast(const DScene& S, int first, int count, const Vec& pt, int* ovf) {  // Csg.hs:99-101
+    for (int i = 0; i < count; i++)
+        if (!gq_inside_fast(S, first + i, pt, ovf)) return false;
+    return true;
+}
+
+// The machine's registers: everything a query keeps between two steps.  (A plain struct of scalars: after inlining the
+// compiler keeps it in registers.)
+struct QRegs {
+    int sp;                 // control stack pointer (words)
+    int nslots, acc;        // hit slots in use; the slot the current fold accumulates into
+    Flt acc_t;              // cached slot[acc].t / .hit
+    bool acc_hit;
+    bool shadow_q;          // the query: shadow (true) or rayint
+    bool smode;             // current evaluation: shadow (any hit) or rayint (closest hit)
+    bool retb;              // a shadow result travelling down the stack
+    int mflags;             // sticky overflow flags of this query
+    int nadv;               // rayint_advance re-issues so far
+    Ray r;
+    Flt d;
+    PStk ctex, ctag;
+    int cur_bih;            // node of the BIH the lin_* registers belong to
+    bool lin_ok;
+    Flt drx, dry, drz;      // 1 / r.d: follows every change of r.d
+    int lin_j0, lin_a0;     // linear sphere block of cur_bih (lin_a0 < 0: none)
+    int ref;
+    Flt near_, far_;
+    int li, ln;             // list registers
+    Flt ld;
+    bool llin;              // the list is a leaf of a linear-sphere BIH
+    int ni;
+    int st;
+};
+
+// Start a query:  shadow_q = false: rayint root ray d [] []  -> result in vm.slot[0] when st == GS_DONE
+//                 shadow_q = true : shadow root ray d        -> q.retb
+GD_FN void qvm_start(QRegs& q, QVM& vm, int root, const Ray& qray, Flt qd, bool shadow_q) {
+    q.sp = 0; q.nslots = 1; q.acc = 0; q.acc_t = GLM_INFINITY; q.acc_hit = false;
+    q.shadow_q = shadow_q; q.smode = shadow_q; q.retb = false; q.mflags = 0; q.nadv = 0;
+    q.r = qray; q.d = qd;
+    q.ctex = pstk_empty(); q.ctag = pstk_empty();
+    q.cur_bih = -1; q.lin_ok = false;
+    q.drx = 1 / qray.d.x; q.dry = 1 / qray.d.y; q.drz = 1 / qray.d.z;
+    q.lin_j0 = 0; q.lin_a0 = -1; q.ref = 0; q.near_ = 0; q.far_ = 0;
+    q.li = 0; q.ln = 0; q.ld = 0; q.llin = false;
+    q.ni = root; q.st = GS_ENTER;
+    ghit_clear(vm.slot[0]);
+    vm.cs[q.sp++] = gq_hdr(GF_ROOT, 0, 0);
+}
+
+// One round of the machine: BIH branch steps, then list items, then at most one ENTER and one RET.  The four parts are
+// laid out one after the other so that the lanes of a warp that sit in the same state execute it together.
+GD_FN void qvm_step(const DScene& S, QRegs& q, QVM& vm, GCnt& cnt) {
     unsigned long long* cs = vm.cs;
     GHit* slot = vm.slot;
-    int sp = 0;                   // control stack pointer (words)
-    int nslots = 1, acc = 0;      // hit slots in use; the slot the current fold accumulates into
-    Flt acc_t = GLM_INFINITY;     // cached slot[acc].t / .hit
-    bool acc_hit = false;
-    bool smode = shadow_q;        // current evaluation: shadow (any hit) or rayint (closest hit)
-    bool retb = false;            // a shadow result travelling down the stack
-    int mflags = 0;               // sticky overflow flags of this query
-    int nadv = 0;                 // rayint_advance re-issues so far
-    Ray r = qray;
-    Flt d = qd;
-    PStk ctex = pstk_empty(), ctag = pstk_empty();
-    // BIH registers
-    int cur_bih = -1;             // node of the BIH they belong to
-    bool inv_ok = false;
-    Flt drx = 0, dry = 0, drz = 0;
-    int lin_j0 = 0, lin_a0 = -1;  // linear sphere block of cur_bih (lin_a0 < 0: none)
-    int ref = 0;
-    Flt near_ = 0, far_ = 0;
-    // list registers
-    int li = 0, ln = 0;
-    Flt ld = 0;
-    bool llin = false;            // the list is a leaf of a linear-sphere BIH
-    int ni = root;
-    int st = GS_ENTER;
-    ghit_clear(slot[0]);
+    int& sp = q.sp; int& nslots = q.nslots; int& acc = q.acc; Flt& acc_t = q.acc_t; bool& acc_hit = q.acc_hit;
+    bool& smode = q.smode; bool& retb = q.retb; int& mflags = q.mflags; int& nadv = q.nadv;
+    Ray& r = q.r; Flt& d = q.d; PStk& ctex = q.ctex; PStk& ctag = q.ctag;
+    int& cur_bih = q.cur_bih; bool& lin_ok = q.lin_ok; Flt& drx = q.drx; Flt& dry = q.dry; Flt& drz = q.drz;
+    int& lin_j0 = q.lin_j0; int& lin_a0 = q.lin_a0; int& ref = q.ref; Flt& near_ = q.near_; Flt& far_ = q.far_;
+    int& li = q.li; int& ln = q.ln; Flt& ld = q.ld; bool& llin = q.llin; int& ni = q.ni; int& st = q.st;
 
 #define GQ_NEED(nw) if (sp + (nw) > GQ_WORDS) { mflags |= GLOME_HITFLAG_CSG_OVERFLOW; goto gq_abort; }
 #define GQ_NEED_SLOT(k) if (nslots + (k) > GQ_SLOTS) { mflags |= GLOME_HITFLAG_CSG_OVERFLOW; goto gq_abort; }
@@ -416,439 +554,373 @@ GD_NOINLINE bool gq_query(const DScene& S, QVM& vm, int root, const Ray& qray, F
         st = GS_LIST;                                                          \
     } while (0)
 
-    cs[sp++] = gq_hdr(GF_ROOT, 0, 0);
 
-    for (;;) {
-        // ---------------- BRANCH: BIH nodes (Bih.hs:340-366 / 516-542) ----------------
-        while (st == GS_BRANCH) {
-            cnt.bih++;
-            const double2* np_ = reinterpret_cast<const double2*>(S.bih + ref);
-            const double2 sp2 = gd_ldg(np_);
-            const int4 ii = gd_ldg(reinterpret_cast<const int4*>(np_ + 1));
-            const Flt dr_ = (ii.x == 0) ? drx : ((ii.x == 1) ? dry : drz);
-            const Flt o = (ii.x == 0) ? r.o.x : ((ii.x == 1) ? r.o.y : r.o.z);
-            const Flt dl = (sp2.x - o) * dr_;
-            const Flt dr = (sp2.y - o) * dr_;
-            const bool fwd = dr_ > 0;       // the near child is the left one iff dirr > 0
-            const Flt dn = fwd ? dl : dr;
-            const Flt df = fwd ? dr : dl;
-            const int c1 = fwd ? ii.y : ii.z;
-            const int c2 = fwd ? ii.z : ii.y;
-            const bool v1 = near_ < dn;
-            const Flt f1 = fmin_(dn, far_);
-            bool v2 = df < far_;
-            const Flt n2 = fmax_(df, near_);
-            if (!smode && v2 && acc_hit && n2 > acc_t) v2 = false;  // best-hit culling
-            if (v1 && v2) {
-                GQ_NEED(3);
-                cs[sp] = gq_d2w(far_); cs[sp + 1] = gq_d2w(n2);
-                cs[sp + 2] = (unsigned long long)GF_TRAV | ((unsigned long long)(unsigned int)c2 << 32);
-                sp += 3;
-            }
-            if (v1) { ref = c1; far_ = f1; }
-            else if (v2) { ref = c2; near_ = n2; }
-            else { st = GS_RET; break; }
-            if (ref < 0) GQ_LEAF();
+    // ---------------- BRANCH: BIH nodes (Bih.hs:340-366 / 516-542) ----------------
+    while (st == GS_BRANCH) {
+        cnt.bih++;
+        const double2* np_ = reinterpret_cast<const double2*>(S.bih + ref);
+        const double2 sp2 = gd_ldg(np_);
+        const int4 ii = gd_ldg(reinterpret_cast<const int4*>(np_ + 1));
+        const Flt dr_ = (ii.x == 0) ? drx : ((ii.x == 1) ? dry : drz);
+        const Flt o = (ii.x == 0) ? r.o.x : ((ii.x == 1) ? r.o.y : r.o.z);
+        const Flt dl = (sp2.x - o) * dr_;
+        const Flt dr = (sp2.y - o) * dr_;
+        const bool fwd = dr_ > 0;       // the near child is the left one iff dirr > 0
+        const Flt dn = fwd ? dl : dr;
+        const Flt df = fwd ? dr : dl;
+        const int c1 = fwd ? ii.y : ii.z;
+        const int c2 = fwd ? ii.z : ii.y;
+        const bool v1 = near_ < dn;
+        const Flt f1 = fmin_(dn, far_);
+        bool v2 = df < far_;
+        const Flt n2 = fmax_(df, near_);
+        if (!smode && v2 && acc_hit && n2 > acc_t) v2 = false;  // best-hit culling
+        if (v1 && v2) {
+            GQ_NEED(3);
+            cs[sp] = gq_d2w(far_); cs[sp + 1] = gq_d2w(n2);
+            cs[sp + 2] = (unsigned long long)GF_TRAV | ((unsigned long long)(unsigned int)c2 << 32);
+            sp += 3;
         }
-        // ---------------- LIST: one item of a group / BIH leaf (Solid.hs:326-331) ----------------
-        if (st == GS_LIST) {
-            if (li >= ln) st = GS_RET;
-            else if (llin) {  // bare sphere of a linear block: no node record to chase
-                const int item = li++;
-                cnt.prim++;
-                const double* sph = S.dpool + lin_a0 + 4 * (item - lin_j0);
-                if (smode) {
-                    if (shadow_sphere(sph, r, ld)) { retb = true; st = GS_RET; }
-                } else {
-                    Flt t; Vec pos, n;
-                    if (prim_sphere<true>(sph, r, ld, t, pos, n) && (!acc_hit || !(acc_t < t))) {
-                        GHit& a = slot[acc];
-                        a.hit = 1; a.t = t; a.pos = pos; a.norm = n; a.ray = r; a.tex = ctex; a.tag = ctag; a.prim = item; a.sub = -1;
-                        acc_t = t; acc_hit = true;
-                    }
-                }
+        if (v1) { ref = c1; far_ = f1; }
+        else if (v2) { ref = c2; near_ = n2; }
+        else { st = GS_RET; break; }
+        if (ref < 0) GQ_LEAF();
+    }
+    // ---------------- LIST: the items of a group / BIH leaf (Solid.hs:326-331) ----------------
+    while (st == GS_LIST) {
+        if (li >= ln) { st = GS_RET; break; }
+        const int item = li++;
+        if (llin) {  // bare sphere of a linear block: no record to chase
+            cnt.prim++;
+            const double* sph = S.dpool + lin_a0 + 4 * (item - lin_j0);
+            if (smode) {
+                if (shadow_sphere(sph, r, ld)) { retb = true; st = GS_RET; }
             } else {
-                const int item = li++;
-                // peel the wrappers that are transparent to this query
-                int cj = item;
-                GlomeNode c = S.nodes[cj];
-                int nw = 0;
-                while (smode ? is_wrap_s(c.type) : is_wrap_r(c.type)) { nw += (c.type == GLOME_TEX || c.type == GLOME_TAG); cj = c.a; c = S.nodes[cj]; }
-                int inst = -1;
-                const Flt* xfm = nullptr;
-                bool simple = is_prim(c.type);
-                const bool dead = c.type == GLOME_VOID ||
-                                  (smode ? (c.type == GLOME_NOSHADOW || c.type == GLOME_MESH) : c.type == GLOME_ONLYSHADOW);
-                Ray tr = r;
-                Flt td = ld, invls = 1;
-                if (c.type == GLOME_INSTANCE) {  // Instance of a wrapped primitive: no frame (oak leaves, cone / cylinder)
-                    int ck = c.a;
-                    GlomeNode cc = S.nodes[ck];
-                    int nw2 = 0;
-                    while (smode ? is_wrap_s(cc.type) : is_wrap_r(cc.type)) { nw2 += (cc.type == GLOME_TEX || cc.type == GLOME_TAG); ck = cc.a; cc = S.nodes[ck]; }
-                    if (is_prim(cc.type)) {
-                        cnt.inst++;
-                        inst = cj;
-                        xfm = S.dpool + c.b;  // Solid.hs:388-403
-                        const Vec newdir = invxfm_vec(xfm, r.d);
-                        const Vec neworig = invxfm_point(xfm, r.o);
-                        const Flt lenscale = vlen(newdir);
-                        invls = 1 / lenscale;
-                        tr = mkray(neworig, vscale(newdir, invls));
-                        td = ld * lenscale;
-                        cj = ck; c = cc; nw += nw2;
-                        simple = true;
-                    }
+                Flt t; Vec pos, n;
+                if (prim_sphere<true>(sph, r, ld, t, pos, n) && (!acc_hit || !(acc_t < t))) {
+                    GHit& a = slot[acc];
+                    a.hit = 1; a.t = t; a.pos = pos; a.norm = n; a.ray = r; a.tex = ctex; a.tag = ctag; a.prim = item; a.sub = -1;
+                    acc_t = t; acc_hit = true;
                 }
-                if (simple) {
-                    cnt.prim++;
-                    if (smode) {
-                        if (prim_shadow(S, c, tr, td)) { retb = true; st = GS_RET; }
-                    } else {
-                        Flt t; Vec pos, n;
-                        if (prim_rayint<true>(S, c, tr, td, t, pos, n)) {
-                            const Flt tw = inst >= 0 ? t * invls : t;
-                            if (!acc_hit || !(acc_t < tw)) {
-                                GHit& a = slot[acc];
-                                a.hit = 1; a.t = tw; a.ray = tr; a.prim = cj; a.sub = -1;
-                                if (inst >= 0) { a.pos = xfm_point(xfm, pos); a.norm = vnorm(invxfm_norm(xfm, n)); }
-                                else { a.pos = pos; a.norm = n; }
-                                PStk tx = ctex, tg = ctag;
-                                if (nw) {  // the winner's wrappers, outermost first (Tex.hs:54,66)
-                                    int wj = item;
-                                    GlomeNode w = S.nodes[wj];
-                                    for (;;) {
-                                        if (w.type == GLOME_TEX) { if (pstk_cons(tx, w.b)) mflags |= GLOME_HITFLAG_STACK_OVERFLOW; }
-                                        else if (w.type == GLOME_TAG) { if (pstk_cons(tg, w.b)) mflags |= GLOME_HITFLAG_STACK_OVERFLOW; }
-                                        else if (w.type == GLOME_NOSHADOW || wj == inst) {}
-                                        else break;
-                                        wj = w.a; w = S.nodes[wj];
-                                    }
-                                }
-                                a.tex = tx; a.tag = tg;
-                                acc_t = tw; acc_hit = true;
-                            }
-                        }
-                    }
-                } else if (!dead) {
-                    // a complex item: remember where the list stands, evaluate the item with the list's distance
-                    GQ_NEED(3);
-                    cs[sp] = gq_d2w(d); cs[sp + 1] = gq_d2w(ld); cs[sp + 2] = gq_hdr(GF_LIST, li, ln);
-                    sp += 3;
-                    ni = item; d = ld; st = GS_ENTER;
-                }
-            }
-        }
-        // ---------------- ENTER: dispatch on a node ----------------
-        if (st == GS_ENTER) {
-            GlomeNode nd = S.nodes[ni];
-            {
-                int nwrap = 0;
-                int cj = ni;
-                GlomeNode c = nd;
-                while (smode ? is_wrap_s(c.type) : is_wrap_r(c.type)) { nwrap += (c.type == GLOME_TEX || c.type == GLOME_TAG); cj = c.a; c = S.nodes[cj]; }
-                bool simple = is_prim(c.type);
-                if (c.type == GLOME_INSTANCE) {
-                    GlomeNode cc = S.nodes[c.a];
-                    while (smode ? is_wrap_s(cc.type) : is_wrap_r(cc.type)) cc = S.nodes[cc.a];
-                    simple = is_prim(cc.type);
-                }
-                if (simple) {  // a one-element list: the primitive test lives in LIST only
-                    li = ni; ln = ni + 1; ld = d; llin = false; st = GS_LIST;
-                    continue;
-                }
-                if (!smode && nwrap) {  // push the wrappers onto the context (Tex.hs:54,66); GF_CTX restores it
-                    GQ_NEED(5);
-                    cs[sp] = ctex.lo; cs[sp + 1] = ctex.hi; cs[sp + 2] = ctag.lo; cs[sp + 3] = ctag.hi; cs[sp + 4] = gq_hdr(GF_CTX, 0, 0);
-                    sp += 5;
-                    GlomeNode w = nd;
-                    while (is_wrap_r(w.type)) {
-                        if (w.type == GLOME_TEX) { if (pstk_cons(ctex, w.b)) mflags |= GLOME_HITFLAG_STACK_OVERFLOW; }
-                        else if (w.type == GLOME_TAG) { if (pstk_cons(ctag, w.b)) mflags |= GLOME_HITFLAG_STACK_OVERFLOW; }
-                        w = S.nodes[w.a];
-                    }
-                }
-                ni = cj; nd = c;
-            }
-            switch (nd.type) {
-                case GLOME_GROUP:  // Solid.hs:327-330
-                    li = nd.a; ln = nd.a + nd.b; ld = d; llin = false; st = GS_LIST;
-                    break;
-                case GLOME_BIH: {  // Bih.hs:332-338, 368 / 510-515, 544
-                    const Bbox bb = ldbb(S.dpool + nd.b);
-                    Flt nr, fr;
-                    bbclip_ub(r, bb, nr, fr);
-                    fr = fmin_(d, fr);
-                    if (nr < 0) nr = 0;  // origin clamp
-                    if (nd.a >= 0 && nr > fr) { st = GS_RET; break; }  // Bih.hs:347 at the root
-                    GQ_NEED(1);
-                    cs[sp++] = gq_hdr(GF_BIH, cur_bih, 0);
-                    cur_bih = ni;
-                    drx = 1 / r.d.x; dry = 1 / r.d.y; drz = 1 / r.d.z;
-                    lin_a0 = -1;
-                    if (nd.c & GLOME_BIH_LINEAR_SPHERES) { lin_j0 = nd.c >> 4; lin_a0 = S.nodes[lin_j0].a; }
-                    inv_ok = true;
-                    ref = nd.a; near_ = nr; far_ = fr;
-                    if (ref < 0) GQ_LEAF();
-                    else st = GS_BRANCH;
-                    break;
-                }
-                case GLOME_MESH: {  // Mesh.hs:136-198; shadow = False (Mesh.hs:210)
-                    if (smode) { st = GS_RET; break; }
-                    Hit mh;
-                    hit_clear(mh);
-                    mh.hit = acc_hit ? 1 : 0; mh.t = acc_t;  // only a hit that beats the fold so far replaces it
-                    Stk tx, tg;
-                    pstk_to_stk(ctex, tx);
-                    pstk_to_stk(ctag, tg);
-                    Cnt mc = {0, 0, 0, 0};
-                    rayint_mesh(S, ni, nd, r, d, tx, tg, true, mh, &mc);
-                    cnt.bvh += mc.bvh; cnt.tri += mc.tri;
-                    mflags |= mh.flags;
-                    if (mh.sub >= 0) {
-                        GHit& a = slot[acc];
-                        a.hit = 1; a.t = mh.t; a.pos = mh.pos; a.norm = mh.norm; a.ray = r; a.prim = ni; a.sub = mh.sub;
-                        if (pstk_from_stk(a.tex, mh.tex)) mflags |= GLOME_HITFLAG_STACK_OVERFLOW;
-                        if (pstk_from_stk(a.tag, mh.tag)) mflags |= GLOME_HITFLAG_STACK_OVERFLOW;
-                        acc_t = mh.t; acc_hit = true;
-                    }
-                    st = GS_RET;
-                    break;
-                }
-                case GLOME_INSTANCE: {  // Solid.hs:388-403 / 464-471
-                    cnt.inst++;
-                    const Flt* xfm = S.dpool + nd.b;
-                    const Vec newdir = invxfm_vec(xfm, r.d);
-                    const Vec neworig = invxfm_point(xfm, r.o);
-                    const Flt lenscale = vlen(newdir);
-                    const Flt invls = 1 / lenscale;
-                    GQ_NEED(9);
-                    cs[sp] = gq_d2w(r.o.x); cs[sp + 1] = gq_d2w(r.o.y); cs[sp + 2] = gq_d2w(r.o.z);
-                    cs[sp + 3] = gq_d2w(r.d.x); cs[sp + 4] = gq_d2w(r.d.y); cs[sp + 5] = gq_d2w(r.d.z);
-                    cs[sp + 6] = gq_d2w(d); cs[sp + 7] = gq_d2w(invls);
-                    cs[sp + 8] = gq_hdr(GF_INST, ni, acc);
-                    sp += 9;
-                    if (!smode) {
-                        GQ_NEED_SLOT(1);
-                        ghit_clear(slot[nslots]);
-                        GQ_SET_ACC(nslots);
-                        nslots++;
-                    }
-                    r = mkray(neworig, vscale(newdir, invls));
-                    d = d * lenscale;
-                    ni = nd.a;
-                    break;  // st stays GS_ENTER
-                }
-                case GLOME_DIFFERENCE:
-                case GLOME_INTERSECTION: {
-                    if (smode) {  // no shadow method: the class default is a rayint with empty stacks (Solid.hs:218-221)
-                        GQ_NEED(6);
-                        GQ_NEED_SLOT(1);
-                        cs[sp] = ctex.lo; cs[sp + 1] = ctex.hi; cs[sp + 2] = ctag.lo; cs[sp + 3] = ctag.hi; cs[sp + 4] = gq_hdr(GF_CTX, 0, 0);
-                        cs[sp + 5] = gq_hdr(GF_MODE, nslots, acc);
-                        sp += 6;
-                        ctex = pstk_empty(); ctag = pstk_empty();
-                        smode = false;
-                        ghit_clear(slot[nslots]);
-                        GQ_SET_ACC(nslots);
-                        nslots++;
-                    }
-                    // result slot R; folded into `acc` when the node is done
-                    GQ_NEED_SLOT(1);
-                    GQ_NEED(7);
-                    const int R = nslots++;
-                    ghit_clear(slot[R]);
-                    cs[sp] = gq_d2w(r.o.x); cs[sp + 1] = gq_d2w(r.o.y); cs[sp + 2] = gq_d2w(r.o.z); cs[sp + 3] = gq_d2w(d);
-                    cs[sp + 4] = gq_hdr(0, R, acc);
-                    sp += 5;
-                    if (nd.type == GLOME_DIFFERENCE) { cs[sp] = gq_hdr(GF_DIFF, ni, 0); sp += 1; }
-                    else { cs[sp] = gq_hdr(GF_ISECT_BASE, ni, 0); cs[sp + 1] = gq_hdr(GF_ISECT, 0, 2); sp += 2; }
-                    st = GS_RET;  // the frame's first phase starts the node
-                    break;
-                }
-                case GLOME_BOUND: {  // Bound.hs:30-35 / 44-49
-                    int ovf = 0;
-                    const bool in = gq_inside(S, nd.a, r.o, &ovf);
-                    if (ovf) mflags |= GLOME_HITFLAG_STACK_OVERFLOW;
-                    if (in) { ni = nd.b; break; }
-                    GQ_NEED(1);
-                    cs[sp++] = gq_hdr(GF_GATE, nd.b, smode ? 1 : 0);
-                    smode = true;
-                    retb = false;
-                    ni = nd.a;
-                    break;
-                }
-                case GLOME_INNERBOUND: {
-                    if (smode) {  // Bound.hs:101-103
-                        GQ_NEED(1);
-                        cs[sp++] = gq_hdr(GF_OR, nd.b, 0);
-                        ni = nd.a;
-                        break;
-                    }
-                    // Bound.hs:98-99: the inner object (empty stacks) only supplies a depth limit for the outer one
-                    GQ_NEED(6);
-                    GQ_NEED_SLOT(1);
-                    cs[sp] = ctex.lo; cs[sp + 1] = ctex.hi; cs[sp + 2] = ctag.lo; cs[sp + 3] = ctag.hi; cs[sp + 4] = gq_d2w(d);
-                    cs[sp + 5] = gq_hdr(GF_INNER, nd.b, acc);
-                    sp += 6;
-                    ctex = pstk_empty(); ctag = pstk_empty();
-                    ghit_clear(slot[nslots]);
-                    GQ_SET_ACC(nslots);
-                    nslots++;
-                    ni = nd.a;
-                    break;
-                }
-                default: st = GS_RET; break;  // Void; OnlyShadow under rayint (Tex.hs:89); NoShadow under shadow (Tex.hs:81)
             }
             continue;
         }
-        // ---------------- RET: pop one continuation ----------------
-        if (st == GS_RET) {
-            const unsigned long long h = cs[--sp];
-            switch (gq_op(h)) {
-                case GF_ROOT: st = GS_DONE; break;
-                case GF_TRAV: {
-                    sp -= 2;
-                    if (smode && retb) break;  // an occluder was found: drop the pending subtrees
-                    const Flt nn = gq_w2d(cs[sp + 1]);
-                    if (!smode && acc_hit && nn > acc_t) break;  // best-hit culling
-                    ref = (int)(unsigned int)(h >> 32);
-                    near_ = nn;
-                    far_ = gq_w2d(cs[sp]);
-                    if (!inv_ok) {  // a nested evaluation used the BIH registers: reload this BIH's invariants
-                        const GlomeNode bn = S.nodes[cur_bih];
-                        drx = 1 / r.d.x; dry = 1 / r.d.y; drz = 1 / r.d.z;
-                        lin_a0 = -1;
-                        if (bn.c & GLOME_BIH_LINEAR_SPHERES) { lin_j0 = bn.c >> 4; lin_a0 = S.nodes[lin_j0].a; }
-                        inv_ok = true;
+        const int4 it = gd_ldg(S.items + item);
+        const int cls = it.x & 15;
+        if (cls == GI_DEAD || !(it.x & (smode ? GI_VIS_S : GI_VIS_R))) continue;  // Void; NoShadow / OnlyShadow / Mesh gates
+        if (cls == GI_COMPLEX) {
+            // remember where the list stands, evaluate the item with the list's distance
+            GQ_NEED(3);
+            cs[sp] = gq_d2w(d); cs[sp + 1] = gq_d2w(ld); cs[sp + 2] = gq_hdr(GF_LIST, li, ln);
+            sp += 3;
+            ni = item; d = ld; st = GS_ENTER;
+            break;
+        }
+        SimpleHit sh_;
+        if (!gq_test_simple(S, it, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, drx, dry, drz, ld, smode, &sh_, &cnt)) continue;
+        if (smode) { retb = true; st = GS_RET; continue; }
+        if (acc_hit && acc_t < sh_.t) continue;
+        gq_fill_hit(S, slot[acc], it, item, sh_, ctex, ctag, mflags);
+        acc_t = sh_.t; acc_hit = true;
+    }
+    // ---------------- ENTER: dispatch on a node ----------------
+    if (st == GS_ENTER) {
+        const int4 it = gd_ldg(S.items + ni);
+        const int cls = it.x & 15;
+        if (cls == GI_PRIM || cls == GI_INST_PRIM) {  // a one-element list: the primitive test lives in LIST only
+            li = ni; ln = ni + 1; ld = d; llin = false; st = GS_LIST;
+            return;
+        }
+        if (cls == GI_DEAD || !(it.x & (smode ? GI_VIS_S : GI_VIS_R))) { st = GS_RET; return; }  // Tex.hs:81,89; Mesh.hs:210
+        if (!smode && (it.x & GI_WRAPPED)) {  // push the wrappers onto the context (Tex.hs:54,66); GF_CTX restores it
+            GQ_NEED(5);
+            cs[sp] = ctex.lo; cs[sp + 1] = ctex.hi; cs[sp + 2] = ctag.lo; cs[sp + 3] = ctag.hi; cs[sp + 4] = gq_hdr(GF_CTX, 0, 0);
+            sp += 5;
+            int wj = ni;
+            while (wj != it.y) {
+                const GlomeNode w = S.nodes[wj];
+                if (w.type == GLOME_TEX) { if (pstk_cons(ctex, w.b)) mflags |= GLOME_HITFLAG_STACK_OVERFLOW; }
+                else if (w.type == GLOME_TAG) { if (pstk_cons(ctag, w.b)) mflags |= GLOME_HITFLAG_STACK_OVERFLOW; }
+                wj = w.a;
+            }
+        }
+        ni = it.y;
+        const GlomeNode nd = S.nodes[ni];
+        switch (nd.type) {
+            case GLOME_GROUP:  // Solid.hs:327-330
+                li = nd.a; ln = nd.a + nd.b; ld = d; llin = false; st = GS_LIST;
+                break;
+            case GLOME_BIH: {  // Bih.hs:332-338, 368 / 510-515, 544
+                const Bbox bb = ldbb(S.dpool + nd.b);
+                Flt nr, fr;
+                bbclip_ub_pre(r, drx, dry, drz, bb, nr, fr);
+                fr = fmin_(d, fr);
+                if (nr < 0) nr = 0;  // origin clamp
+                if (nd.a >= 0 && nr > fr) { st = GS_RET; break; }  // Bih.hs:347 at the root
+                GQ_NEED(1);
+                cs[sp++] = gq_hdr(GF_BIH, cur_bih, 0);
+                cur_bih = ni;
+                lin_a0 = -1;
+                if (nd.c & GLOME_BIH_LINEAR_SPHERES) { lin_j0 = nd.c >> 4; lin_a0 = S.nodes[lin_j0].a; }
+                lin_ok = true;
+                ref = nd.a; near_ = nr; far_ = fr;
+                if (ref < 0) GQ_LEAF();
+                else st = GS_BRANCH;
+                break;
+            }
+            case GLOME_MESH: {  // Mesh.hs:136-198; shadow = False (Mesh.hs:210)
+                if (smode) { st = GS_RET; break; }
+                Hit mh;
+                hit_clear(mh);
+                mh.hit = acc_hit ? 1 : 0; mh.t = acc_t;  // only a hit that beats the fold so far replaces it
+                Stk tx, tg;
+                pstk_to_stk(ctex, tx);
+                pstk_to_stk(ctag, tg);
+                Cnt mc = {0, 0, 0, 0};
+                rayint_mesh(S, ni, nd, r, d, tx, tg, true, mh, &mc);
+                cnt.bvh += mc.bvh; cnt.tri += mc.tri;
+                mflags |= mh.flags;
+                if (mh.sub >= 0) {
+                    GHit& a = slot[acc];
+                    a.hit = 1; a.t = mh.t; a.pos = mh.pos; a.norm = mh.norm; a.ray = r; a.prim = ni; a.sub = mh.sub;
+                    if (pstk_from_stk(a.tex, mh.tex)) mflags |= GLOME_HITFLAG_STACK_OVERFLOW;
+                    if (pstk_from_stk(a.tag, mh.tag)) mflags |= GLOME_HITFLAG_STACK_OVERFLOW;
+                    acc_t = mh.t; acc_hit = true;
+                }
+                st = GS_RET;
+                break;
+            }
+            case GLOME_INSTANCE: {  // Solid.hs:388-403 / 464-471
+                cnt.inst++;
+                const Flt* xfm = S.dpool + nd.b;
+                const Vec newdir = invxfm_vec(xfm, r.d);
+                const Vec neworig = invxfm_point(xfm, r.o);
+                const Flt lenscale = vlen(newdir);
+                const Flt invls = 1 / lenscale;
+                GQ_NEED(12);
+                cs[sp] = gq_d2w(r.o.x); cs[sp + 1] = gq_d2w(r.o.y); cs[sp + 2] = gq_d2w(r.o.z);
+                cs[sp + 3] = gq_d2w(r.d.x); cs[sp + 4] = gq_d2w(r.d.y); cs[sp + 5] = gq_d2w(r.d.z);
+                cs[sp + 6] = gq_d2w(d); cs[sp + 7] = gq_d2w(invls);
+                cs[sp + 8] = gq_d2w(drx); cs[sp + 9] = gq_d2w(dry); cs[sp + 10] = gq_d2w(drz);
+                cs[sp + 11] = gq_hdr(GF_INST, ni, acc);
+                sp += 12;
+                if (!smode) {
+                    GQ_NEED_SLOT(1);
+                    ghit_clear(slot[nslots]);
+                    GQ_SET_ACC(nslots);
+                    nslots++;
+                }
+                r = mkray(neworig, vscale(newdir, invls));
+                drx = 1 / r.d.x; dry = 1 / r.d.y; drz = 1 / r.d.z;
+                d = d * lenscale;
+                ni = nd.a;
+                break;  // st stays GS_ENTER
+            }
+            case GLOME_DIFFERENCE:
+            case GLOME_INTERSECTION: {
+                if (smode) {  // no shadow method: the class default is a rayint with empty stacks (Solid.hs:218-221)
+                    GQ_NEED(6);
+                    GQ_NEED_SLOT(1);
+                    cs[sp] = ctex.lo; cs[sp + 1] = ctex.hi; cs[sp + 2] = ctag.lo; cs[sp + 3] = ctag.hi; cs[sp + 4] = gq_hdr(GF_CTX, 0, 0);
+                    cs[sp + 5] = gq_hdr(GF_MODE, nslots, acc);
+                    sp += 6;
+                    ctex = pstk_empty(); ctag = pstk_empty();
+                    smode = false;
+                    ghit_clear(slot[nslots]);
+                    GQ_SET_ACC(nslots);
+                    nslots++;
+                }
+                // result slot R; folded into `acc` when the node is done
+                GQ_NEED_SLOT(1);
+                GQ_NEED(7);
+                const int R = nslots++;
+                ghit_clear(slot[R]);
+                cs[sp] = gq_d2w(r.o.x); cs[sp + 1] = gq_d2w(r.o.y); cs[sp + 2] = gq_d2w(r.o.z); cs[sp + 3] = gq_d2w(d);
+                cs[sp + 4] = gq_hdr(0, R, acc);
+                sp += 5;
+                if (nd.type == GLOME_DIFFERENCE) { cs[sp] = gq_hdr(GF_DIFF, ni, 0); sp += 1; }
+                else { cs[sp] = gq_hdr(GF_ISECT_BASE, ni, 0); cs[sp + 1] = gq_hdr(GF_ISECT, 0, 2); sp += 2; }
+                st = GS_RET;  // the frame's first phase starts the node
+                break;
+            }
+            case GLOME_BOUND: {  // Bound.hs:30-35 / 44-49
+                int ovf = 0;
+                const bool in = gq_inside(S, nd.a, r.o, &ovf);
+                if (ovf) mflags |= GLOME_HITFLAG_STACK_OVERFLOW;
+                if (in) { ni = nd.b; break; }
+                GQ_NEED(1);
+                cs[sp++] = gq_hdr(GF_GATE, nd.b, smode ? 1 : 0);
+                smode = true;
+                retb = false;
+                ni = nd.a;
+                break;
+            }
+            case GLOME_INNERBOUND: {
+                if (smode) {  // Bound.hs:101-103
+                    GQ_NEED(1);
+                    cs[sp++] = gq_hdr(GF_OR, nd.b, 0);
+                    ni = nd.a;
+                    break;
+                }
+                // Bound.hs:98-99: the inner object (empty stacks) only supplies a depth limit for the outer one
+                GQ_NEED(6);
+                GQ_NEED_SLOT(1);
+                cs[sp] = ctex.lo; cs[sp + 1] = ctex.hi; cs[sp + 2] = ctag.lo; cs[sp + 3] = ctag.hi; cs[sp + 4] = gq_d2w(d);
+                cs[sp + 5] = gq_hdr(GF_INNER, nd.b, acc);
+                sp += 6;
+                ctex = pstk_empty(); ctag = pstk_empty();
+                ghit_clear(slot[nslots]);
+                GQ_SET_ACC(nslots);
+                nslots++;
+                ni = nd.a;
+                break;
+            }
+            default: st = GS_RET; break;  // Void; OnlyShadow under rayint (Tex.hs:89); NoShadow under shadow (Tex.hs:81)
+        }
+        return;
+    }
+    // ---------------- RET: pop one continuation ----------------
+    if (st == GS_RET) {
+        const unsigned long long h = cs[--sp];
+        switch (gq_op(h)) {
+            case GF_ROOT:
+                slot[0].flags |= mflags;
+                st = GS_DONE;
+                break;
+            case GF_TRAV: {
+                sp -= 2;
+                if (smode && retb) break;  // an occluder was found: drop the pending subtrees
+                const Flt nn = gq_w2d(cs[sp + 1]);
+                if (!smode && acc_hit && nn > acc_t) break;  // best-hit culling
+                ref = (int)(unsigned int)(h >> 32);
+                near_ = nn;
+                far_ = gq_w2d(cs[sp]);
+                if (!lin_ok) {  // a nested BIH used the registers: reload this BIH's
+                    const GlomeNode bn = S.nodes[cur_bih];
+                    lin_a0 = -1;
+                    if (bn.c & GLOME_BIH_LINEAR_SPHERES) { lin_j0 = bn.c >> 4; lin_a0 = S.nodes[lin_j0].a; }
+                    lin_ok = true;
+                }
+                if (ref < 0) GQ_LEAF();
+                else st = GS_BRANCH;
+                break;
+            }
+            case GF_BIH:
+                cur_bih = gq_a(h);
+                lin_ok = false;
+                break;
+            case GF_LIST:
+                sp -= 2;
+                d = gq_w2d(cs[sp]);
+                if (smode && retb) break;
+                li = gq_a(h); ln = gq_b(h); ld = gq_w2d(cs[sp + 1]);
+                llin = false;  // a list holding a complex item is never a linear-sphere leaf
+                st = GS_LIST;
+                break;
+            case GF_CTX:
+                sp -= 4;
+                ctex.lo = cs[sp]; ctex.hi = cs[sp + 1]; ctag.lo = cs[sp + 2]; ctag.hi = cs[sp + 3];
+                break;
+            case GF_INST: {
+                sp -= 11;
+                const int node = gq_a(h), parent = gq_b(h);
+                r.o = vec(gq_w2d(cs[sp]), gq_w2d(cs[sp + 1]), gq_w2d(cs[sp + 2]));
+                r.d = vec(gq_w2d(cs[sp + 3]), gq_w2d(cs[sp + 4]), gq_w2d(cs[sp + 5]));
+                d = gq_w2d(cs[sp + 6]);
+                drx = gq_w2d(cs[sp + 8]); dry = gq_w2d(cs[sp + 9]); drz = gq_w2d(cs[sp + 10]);
+                if (smode) break;
+                const Flt invls = gq_w2d(cs[sp + 7]);
+                const GHit& c = slot[acc];
+                GHit& p = slot[parent];
+                if (c.hit) {
+                    const Flt t = c.t * invls;
+                    if (!p.hit || !(p.t < t)) {
+                        const Flt* xfm = S.dpool + S.nodes[node].b;
+                        p.hit = 1; p.t = t;
+                        p.pos = xfm_point(xfm, c.pos);
+                        p.norm = vnorm(invxfm_norm(xfm, c.norm));
+                        p.ray = c.ray; p.tex = c.tex; p.tag = c.tag; p.prim = c.prim; p.sub = c.sub;
                     }
-                    if (ref < 0) GQ_LEAF();
-                    else st = GS_BRANCH;
-                    break;
                 }
-                case GF_BIH:
-                    cur_bih = gq_a(h);
-                    inv_ok = false;
-                    break;
-                case GF_LIST:
-                    sp -= 2;
-                    d = gq_w2d(cs[sp]);
-                    if (smode && retb) break;
-                    li = gq_a(h); ln = gq_b(h); ld = gq_w2d(cs[sp + 1]);
-                    llin = false;  // a list holding a complex item is never a linear-sphere leaf
-                    st = GS_LIST;
-                    break;
-                case GF_CTX:
-                    sp -= 4;
-                    ctex.lo = cs[sp]; ctex.hi = cs[sp + 1]; ctag.lo = cs[sp + 2]; ctag.hi = cs[sp + 3];
-                    break;
-                case GF_INST: {
-                    sp -= 8;
-                    const int node = gq_a(h), parent = gq_b(h);
-                    r.o = vec(gq_w2d(cs[sp]), gq_w2d(cs[sp + 1]), gq_w2d(cs[sp + 2]));
-                    r.d = vec(gq_w2d(cs[sp + 3]), gq_w2d(cs[sp + 4]), gq_w2d(cs[sp + 5]));
-                    d = gq_w2d(cs[sp + 6]);
-                    inv_ok = false;
-                    if (smode) break;
-                    const Flt invls = gq_w2d(cs[sp + 7]);
-                    const GHit& c = slot[acc];
-                    GHit& p = slot[parent];
-                    if (c.hit) {
-                        const Flt t = c.t * invls;
-                        if (!p.hit || !(p.t < t)) {
-                            const Flt* xfm = S.dpool + S.nodes[node].b;
-                            p.hit = 1; p.t = t;
-                            p.pos = xfm_point(xfm, c.pos);
-                            p.norm = vnorm(invxfm_norm(xfm, c.norm));
-                            p.ray = c.ray; p.tex = c.tex; p.tag = c.tag; p.prim = c.prim; p.sub = c.sub;
-                        }
-                    }
-                    nslots--;
-                    GQ_SET_ACC(parent);
-                    break;
-                }
-                case GF_MODE: {  // the rayint that stood in for a shadow is done: its hit flag is the answer
-                    const int sl = gq_a(h);
-                    retb = slot[sl].hit != 0;
-                    nslots = sl;
-                    smode = true;
-                    GQ_SET_ACC(gq_b(h));
-                    break;
-                }
-                case GF_GATE: {
-                    const bool pass = retb;
-                    smode = gq_b(h) != 0;
-                    retb = false;
-                    if (pass) { ni = gq_a(h); st = GS_ENTER; }
-                    break;
-                }
-                case GF_OR:
-                    if (!retb) { ni = gq_a(h); st = GS_ENTER; }
-                    break;
-                case GF_INNER: {
-                    sp -= 5;
-                    ctex.lo = cs[sp]; ctex.hi = cs[sp + 1]; ctag.lo = cs[sp + 2]; ctag.hi = cs[sp + 3];
-                    const Flt dsave = gq_w2d(cs[sp + 4]);
-                    const Flt dn = ghit_depth(slot[acc]);  // Bound.hs:99
-                    nslots--;
-                    GQ_SET_ACC(gq_b(h));
-                    cs[sp] = gq_d2w(dsave); cs[sp + 1] = gq_hdr(GF_SETD, 0, 0);  // (reuses the words just popped)
-                    sp += 2;
-                    d = dn;
-                    ni = gq_a(h);
-                    st = GS_ENTER;
-                    break;
-                }
-                case GF_SETD:
-                    sp -= 1;
-                    d = gq_w2d(cs[sp]);
-                    break;
-                case GF_DIFF: {  // Csg.hs:33-54
-                    const int node = gq_a(h), phase = gq_b(h);
-                    int bp = sp - 1;
-                    while (gq_op(cs[bp]) == GF_ADD) bp -= 2;
-                    const int R = gq_a(cs[bp]), parent = gq_b(cs[bp]);
-                    const GlomeNode nd = S.nodes[node];
-                    const int sa = nd.a, sb = nd.b;
-                    const int X = R + 1, Y = R + 2;  // sub-results live right above R
-                    int ovf = 0;
+                nslots--;
+                GQ_SET_ACC(parent);
+                break;
+            }
+            case GF_MODE: {  // the rayint that stood in for a shadow is done: its hit flag is the answer
+                const int sl = gq_a(h);
+                retb = slot[sl].hit != 0;
+                nslots = sl;
+                smode = true;
+                GQ_SET_ACC(gq_b(h));
+                break;
+            }
+            case GF_GATE: {
+                const bool pass = retb;
+                smode = gq_b(h) != 0;
+                retb = false;
+                if (pass) { ni = gq_a(h); st = GS_ENTER; }
+                break;
+            }
+            case GF_OR:
+                if (!retb) { ni = gq_a(h); st = GS_ENTER; }
+                break;
+            case GF_INNER: {
+                sp -= 5;
+                ctex.lo = cs[sp]; ctex.hi = cs[sp + 1]; ctag.lo = cs[sp + 2]; ctag.hi = cs[sp + 3];
+                const Flt dsave = gq_w2d(cs[sp + 4]);
+                const Flt dn = ghit_depth(slot[acc]);  // Bound.hs:99
+                nslots--;
+                GQ_SET_ACC(gq_b(h));
+                cs[sp] = gq_d2w(dsave); cs[sp + 1] = gq_hdr(GF_SETD, 0, 0);  // (reuses the words just popped)
+                sp += 2;
+                d = dn;
+                ni = gq_a(h);
+                st = GS_ENTER;
+                break;
+            }
+            case GF_SETD:
+                sp -= 1;
+                d = gq_w2d(cs[sp]);
+                break;
+            case GF_DIFF: {  // Csg.hs:33-54
+                const int node = gq_a(h);
+                int phase = gq_b(h);
+                int bp = sp - 1;
+                while (gq_op(cs[bp]) == GF_ADD) bp -= 2;
+                const int R = gq_a(cs[bp]), parent = gq_b(cs[bp]);
+                const GlomeNode nd = S.nodes[node];
+                const int sa = nd.a, sb = nd.b;
+                const int X = R + 1, Y = R + 2;  // sub-results live right above R
+                int ovf = 0;
+                // The phases run back to back while the operand to evaluate is a simple item (tested right here by
+                // gq_test_simple); a complex operand is ENTERed with this frame re-pushed for the phase that follows.
+                for (;;) {
                     bool finish = false, advance = false;
                     Flt adv = 0;
+                    int want = -1, wslot = X, nphase = 0;  // operand to evaluate next, into which slot, continuing where
                     if (phase == 0) {
                         // inside sb (origin r)  ->  rib = rayint sb ... ; else ria = rayint sa ...
-                        const bool inb = gq_inside(S, sb, r.o, &ovf);
-                        GQ_NEED_SLOT(1);
-                        GQ_NEED(1);
-                        nslots = X + 1;
-                        ghit_clear(slot[X]);
-                        GQ_SET_ACC(X);
-                        cs[sp++] = gq_hdr(GF_DIFF, node, inb ? 1 : 2);
-                        ni = inb ? sb : sa; st = GS_ENTER;
+                        const bool inb = gq_inside_fast(S, sb, r.o, &ovf);
+                        want = inb ? sb : sa; wslot = X; nphase = inb ? 1 : 2;
                     } else if (phase == 1) {  // origin inside sb; rib in X
                         const GHit& rib = slot[X];
                         if (!rib.hit) finish = true;
-                        else if (gq_inside(S, sa, rib.pos, &ovf) && !gq_inside(S, sb, vscaleadd(rib.pos, r.d, GLM_DELTA), &ovf)) {
+                        else if (gq_inside_fast(S, sa, rib.pos, &ovf) && !gq_inside_fast(S, sb, vscaleadd(rib.pos, r.d, GLM_DELTA), &ovf)) {
                             GHit& o = slot[R];
                             o = rib;
                             o.norm = vinvert(rib.norm);
                             if (nd.c != 0) {  // useatex: textures / tags come from get_metainfo sa bp ONLY
-                                int fl = 0;
-                                gq_metainfo(S, sa, rib.pos, o.tex, o.tag, fl);
-                                mflags |= fl;
+                                if (gd_ldg(S.items + sa).x & GI_HAS_META) {
+                                    int fl = 0;
+                                    gq_metainfo(S, sa, rib.pos, o.tex, o.tag, fl);
+                                    mflags |= fl;
+                                } else { o.tex = pstk_empty(); o.tag = pstk_empty(); }  // no Tex / Tag below sa: ([],[])
                             }
                             finish = true;
                         } else { advance = true; adv = rib.t; }
                     } else if (phase == 2) {  // origin outside sb; ria in X
                         if (!slot[X].hit) finish = true;
-                        else {
-                            GQ_NEED_SLOT(1);
-                            GQ_NEED(1);
-                            nslots = Y + 1;
-                            ghit_clear(slot[Y]);
-                            GQ_SET_ACC(Y);
-                            cs[sp++] = gq_hdr(GF_DIFF, node, 3);
-                            ni = sb; st = GS_ENTER;
-                        }
+                        else { want = sb; wslot = Y; nphase = 3; }
                     } else {  // phase 3: ria in X, rib in Y
                         const GHit& ria = slot[X];
                         const GHit& rib = slot[Y];
@@ -857,7 +929,27 @@ GD_NOINLINE bool gq_query(const DScene& S, QVM& vm, int root, const Ray& qray, F
                             else { advance = true; adv = rib.t; }
                         } else { slot[R] = ria; finish = true; }
                     }
-                    if (ovf) mflags |= GLOME_HITFLAG_STACK_OVERFLOW;
+                    if (want >= 0) {
+                        if (wslot + 1 > GQ_SLOTS) { mflags |= GLOME_HITFLAG_CSG_OVERFLOW; goto gq_abort; }
+                        nslots = wslot + 1;
+                        ghit_clear(slot[wslot]);
+                        const int4 wit = gd_ldg(S.items + want);
+                        const int wcls = wit.x & 15;
+                        if (wcls != GI_COMPLEX) {  // rayint of a simple operand, no frame
+                            if (wcls != GI_DEAD && (wit.x & GI_VIS_R)) {
+                                SimpleHit sh_;
+                                if (gq_test_simple(S, wit, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, drx, dry, drz, d, false, &sh_, &cnt))
+                                    gq_fill_hit(S, slot[wslot], wit, want, sh_, ctex, ctag, mflags);
+                            }
+                            phase = nphase;
+                            continue;
+                        }
+                        GQ_NEED(1);
+                        GQ_SET_ACC(wslot);
+                        cs[sp++] = gq_hdr(GF_DIFF, node, nphase);
+                        ni = want; st = GS_ENTER;
+                        break;
+                    }
                     if (advance) {  // rayint_advance (Solid.hs:85-91): re-issue the whole node from adv + delta further on
                         const Flt a = adv + GLM_DELTA;
                         cnt.csg++;
@@ -872,9 +964,9 @@ GD_NOINLINE bool gq_query(const DScene& S, QVM& vm, int root, const Ray& qray, F
                             } else { cs[sp] = gq_d2w(a); cs[sp + 1] = gq_hdr(GF_ADD, 0, 0); sp += 2; }
                             r = ray_move(r, a);
                             d = d - a;
-                            inv_ok = false;
                             nslots = R + 1;
-                            cs[sp++] = gq_hdr(GF_DIFF, node, 0);  // phase 0 again
+                            phase = 0;
+                            continue;
                         }
                     }
                     if (finish) {  // pending offsets innermost first, then the frame's fixed part
@@ -886,7 +978,6 @@ GD_NOINLINE bool gq_query(const DScene& S, QVM& vm, int root, const Ray& qray, F
                         sp -= 5;
                         r.o = vec(gq_w2d(cs[sp]), gq_w2d(cs[sp + 1]), gq_w2d(cs[sp + 2]));
                         d = gq_w2d(cs[sp + 3]);
-                        inv_ok = false;
                         GHit& p = slot[parent];
                         if (o.hit && (!p.hit || !(p.t < o.t))) p = o;
                         nslots = R;
@@ -894,26 +985,34 @@ GD_NOINLINE bool gq_query(const DScene& S, QVM& vm, int root, const Ray& qray, F
                     }
                     break;
                 }
-                case GF_ISECT: {  // Csg.hs:68-90
-                    int k = gq_a(h);
-                    const int pb = gq_b(h);
-                    const int phase = pb & 3, in = (pb >> 2) & 1;
-                    int bp = sp - 1;  // the base of this Intersection: below its ADD / ELSE_ADV entries
-                    for (;;) {
-                        const int op = gq_op(cs[bp]);
-                        if (op == GF_ISECT_BASE) break;
-                        bp -= (op == GF_ADD) ? 2 : 6;
-                    }
-                    const int node = gq_a(cs[bp]);
-                    const int R = gq_a(cs[bp - 1]), parent = gq_b(cs[bp - 1]);
-                    const GlomeNode nd = S.nodes[node];
-                    const int first = nd.a, count = nd.b;
-                    const int X = R + 1;
-                    int ovf = 0;
-                    bool unwind = false;
-                    bool start = phase == 2;
-                    if (phase == 0) unwind = true;  // the last element wrote straight into R
-                    else if (phase == 1) {          // rs = rayint s r d t tags, in X
+                if (ovf) mflags |= GLOME_HITFLAG_STACK_OVERFLOW;
+                break;
+            }
+            case GF_ISECT: {  // Csg.hs:68-90
+                int k = gq_a(h);
+                const int pb = gq_b(h);
+                int phase = pb & 3, in = (pb >> 2) & 1;
+                int bp = sp - 1;  // the base of this Intersection: below its ADD / ELSE_ADV entries
+                for (;;) {
+                    const int op = gq_op(cs[bp]);
+                    if (op == GF_ISECT_BASE) break;
+                    bp -= (op == GF_ADD) ? 2 : 6;
+                }
+                const int node = gq_a(cs[bp]);
+                const int R = gq_a(cs[bp - 1]), parent = gq_b(cs[bp - 1]);
+                const GlomeNode nd = S.nodes[node];
+                const int first = nd.a, count = nd.b;
+                const int X = R + 1;
+                int ovf = 0;
+                bool unwind = false;
+                bool start = phase == 2;
+                if (phase == 0) unwind = true;  // the last element wrote straight into R
+                nslots = R + 1;
+                // As in GF_DIFF: an element that is a simple item is tested right here and the loop goes on; a complex
+                // element is ENTERed with a GF_ISECT frame for the phase that follows.
+                for (;;) {
+                    if (phase == 1) {          // rs = rayint s r d t tags, in X
+                        phase = 3;
                         const GHit& rs = slot[X];
                         if (in) {
                             if (!rs.hit) { k++; start = true; }  // rayint_intersection ss r d
@@ -928,7 +1027,7 @@ GD_NOINLINE bool gq_query(const DScene& S, QVM& vm, int root, const Ray& qray, F
                             }
                         } else {
                             if (!rs.hit) unwind = true;
-                            else if (gq_inside_all(S, first + k + 1, count - k - 1, rs.pos, &ovf)) {
+                            else if (gq_inside_all_fast(S, first + k + 1, count - k - 1, rs.pos, &ovf)) {
                                 slot[R] = rs;
                                 slot[R].ray = r;  // RayHit sd sp sn r vzero st stags (Csg.hs:88)
                                 unwind = true;
@@ -944,98 +1043,108 @@ GD_NOINLINE bool gq_query(const DScene& S, QVM& vm, int root, const Ray& qray, F
                                     } else { cs[sp] = gq_d2w(a); cs[sp + 1] = gq_hdr(GF_ADD, 0, 0); sp += 2; }
                                     r = ray_move(r, a);
                                     d = d - a;
-                                    inv_ok = false;
                                     start = true;  // same k
                                 }
                             }
                         }
+                        nslots = R + 1;
                     }
-                    if (ovf) mflags |= GLOME_HITFLAG_STACK_OVERFLOW;
-                    nslots = R + 1;
-                    for (;;) {
-                        if (start) {
-                            start = false;
-                            const int n = count - k;
-                            if (n <= 0 || d < 0) unwind = true;
-                            else if (n == 1) {  // rayint s r d t tags straight into R
-                                GQ_NEED(1);
-                                ghit_clear(slot[R]);
-                                GQ_SET_ACC(R);
-                                cs[sp++] = gq_hdr(GF_ISECT, k, 0);
-                                ni = first + k; st = GS_ENTER;
-                                break;
-                            } else {
-                                GQ_NEED(1);
-                                GQ_NEED_SLOT(1);
-                                int o2 = 0;
-                                const GlomeNode c = S.nodes[first + k];
-                                const bool inn = is_prim(c.type) ? prim_inside(S, c, r.o) : gq_inside(S, first + k, r.o, &o2);
-                                if (o2) mflags |= GLOME_HITFLAG_STACK_OVERFLOW;
+                    if (start) {
+                        start = false;
+                        const int n = count - k;
+                        if (n <= 0 || d < 0) unwind = true;
+                        else {
+                            const int el = first + k;
+                            const int4 eit = gd_ldg(S.items + el);
+                            const int ecls = eit.x & 15;
+                            const bool last = n == 1;
+                            const int tslot = last ? R : X;   // the last element's rayint is the result itself
+                            bool inn = false;
+                            if (!last) {
+                                if (X + 1 > GQ_SLOTS) { mflags |= GLOME_HITFLAG_CSG_OVERFLOW; goto gq_abort; }
+                                inn = gq_inside_fast(S, el, r.o, &ovf);
                                 nslots = X + 1;
-                                ghit_clear(slot[X]);
-                                GQ_SET_ACC(X);
-                                cs[sp++] = gq_hdr(GF_ISECT, k, 1 | (inn ? 4 : 0));
-                                ni = first + k; st = GS_ENTER;
-                                break;
                             }
+                            ghit_clear(slot[tslot]);
+                            if (ecls != GI_COMPLEX) {
+                                if (ecls != GI_DEAD && (eit.x & GI_VIS_R)) {
+                                    SimpleHit sh_;
+                                    if (gq_test_simple(S, eit, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, drx, dry, drz, d, false, &sh_, &cnt))
+                                        gq_fill_hit(S, slot[tslot], eit, el, sh_, ctex, ctag, mflags);
+                                }
+                                if (last) unwind = true;
+                                else { phase = 1; in = inn ? 1 : 0; }
+                                continue;
+                            }
+                            GQ_NEED(1);
+                            GQ_SET_ACC(tslot);
+                            cs[sp++] = gq_hdr(GF_ISECT, k, last ? 0 : (1 | (inn ? 4 : 0)));
+                            ni = el; st = GS_ENTER;
+                            break;
                         }
-                        if (!unwind) break;
-                        // unwind this Intersection's continuations, top down
-                        GHit& o = slot[R];
-                        const int op = gq_op(cs[sp - 1]);
-                        if (op == GF_ADD) {
-                            if (o.hit) o.t = o.t + gq_w2d(cs[sp - 2]);
-                            sp -= 2;
-                            continue;
-                        }
-                        if (op == GF_ELSE_ADV) {
-                            sp -= 6;
-                            if (o.hit) continue;  // the rest did hit: that is the result
-                            // rayint_advance (SolidItem (Intersection (s:ss))) r d t tags (ridepth rs)
-                            const Flt a = gq_w2d(cs[sp + 4]) + GLM_DELTA;
-                            cnt.csg++;
-                            if (++nadv > GQ_ADV_CAP) { mflags |= GLOME_HITFLAG_CSG_OVERFLOW; continue; }
-                            k = gq_a(cs[sp + 5]);
-                            r.o = vscaleadd(vec(gq_w2d(cs[sp]), gq_w2d(cs[sp + 1]), gq_w2d(cs[sp + 2])), r.d, a);
-                            d = gq_w2d(cs[sp + 3]) - a;
-                            inv_ok = false;
-                            cs[sp] = gq_d2w(a); cs[sp + 1] = gq_hdr(GF_ADD, 0, 0);
-                            sp += 2;
-                            ghit_clear(o);
-                            unwind = false; start = true;
-                            continue;
-                        }
-                        // GF_ISECT_BASE: the node is done
-                        sp -= 6;
-                        r.o = vec(gq_w2d(cs[sp]), gq_w2d(cs[sp + 1]), gq_w2d(cs[sp + 2]));
-                        d = gq_w2d(cs[sp + 3]);
-                        inv_ok = false;
-                        GHit& p = slot[parent];
-                        if (o.hit && (!p.hit || !(p.t < o.t))) p = o;
-                        nslots = R;
-                        GQ_SET_ACC(parent);
-                        break;
                     }
+                    if (!unwind) break;
+                    // unwind this Intersection's continuations, top down
+                    GHit& o = slot[R];
+                    const int op = gq_op(cs[sp - 1]);
+                    if (op == GF_ADD) {
+                        if (o.hit) o.t = o.t + gq_w2d(cs[sp - 2]);
+                        sp -= 2;
+                        continue;
+                    }
+                    if (op == GF_ELSE_ADV) {
+                        sp -= 6;
+                        if (o.hit) continue;  // the rest did hit: that is the result
+                        // rayint_advance (SolidItem (Intersection (s:ss))) r d t tags (ridepth rs)
+                        const Flt a = gq_w2d(cs[sp + 4]) + GLM_DELTA;
+                        cnt.csg++;
+                        if (++nadv > GQ_ADV_CAP) { mflags |= GLOME_HITFLAG_CSG_OVERFLOW; continue; }
+                        k = gq_a(cs[sp + 5]);
+                        r.o = vscaleadd(vec(gq_w2d(cs[sp]), gq_w2d(cs[sp + 1]), gq_w2d(cs[sp + 2])), r.d, a);
+                        d = gq_w2d(cs[sp + 3]) - a;
+                        cs[sp] = gq_d2w(a); cs[sp + 1] = gq_hdr(GF_ADD, 0, 0);
+                        sp += 2;
+                        ghit_clear(o);
+                        unwind = false; start = true;
+                        continue;
+                    }
+                    // GF_ISECT_BASE: the node is done
+                    sp -= 6;
+                    r.o = vec(gq_w2d(cs[sp]), gq_w2d(cs[sp + 1]), gq_w2d(cs[sp + 2]));
+                    d = gq_w2d(cs[sp + 3]);
+                    GHit& p = slot[parent];
+                    if (o.hit && (!p.hit || !(p.t < o.t))) p = o;
+                    nslots = R;
+                    GQ_SET_ACC(parent);
                     break;
                 }
-                default: mflags |= GLOME_HITFLAG_CSG_OVERFLOW; goto gq_abort;  // corrupt stack: cannot happen
+                if (ovf) mflags |= GLOME_HITFLAG_STACK_OVERFLOW;
+                break;
             }
-            continue;
+            default: mflags |= GLOME_HITFLAG_CSG_OVERFLOW; goto gq_abort;  // corrupt stack: cannot happen
         }
-        if (st == GS_DONE) break;
+        return;
     }
-    slot[0].flags |= mflags;
-    return shadow_q ? retb : (slot[0].hit != 0);
+    return;
 
 gq_abort:
     // the control or slot stack is exhausted: a flagged miss rather than a wrong hit
     ghit_clear(slot[0]);
     slot[0].flags = mflags;
-    return false;
+    retb = false;
+    st = GS_DONE;
 #undef GQ_NEED
 #undef GQ_NEED_SLOT
 #undef GQ_SET_ACC
 #undef GQ_LEAF
+}
+
+// Evaluate one query to completion (batch kernels, the pick query, debug counts).
+GD_NOINLINE bool gq_query(const DScene& S, QVM& vm, int root, const Ray& qray, Flt qd, bool shadow_q, GCnt& cnt) {
+    QRegs q;
+    qvm_start(q, vm, root, qray, qd, shadow_q);
+    while (q.st != GS_DONE) qvm_step(S, q, vm, cnt);
+    return shadow_q ? q.retb : (vm.slot[0].hit != 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1189,23 +1298,36 @@ struct SHM {
 };
 struct TagArena { int n, overflow; int v[GS_TAGCAP]; };
 
-enum { SS_T_BEGIN = 0, SS_T_TEX, SS_M_EVAL, SS_M_RET, SS_T_RETURN };
+enum { SS_T_BEGIN = 0, SS_T_HIT, SS_T_TEX, SS_M_EVAL, SS_LIGHTS, SS_LIGHT_RET, SS_M_RET, SS_T_RETURN, SS_FINISHED };
 
-// trace lights shader sld ray depth recurs -> (colour, the TraceResult's tag list when TAGS, primary Rayint)
+// the shading machine's registers
+struct SRegs {
+    int L, msp, st, fl;
+    int m_id;        // material being evaluated (-1: a texture-computed Blend)
+    int li;          // mpreshade's light loop
+    ColorA rv_c;     // value returned by the last material / trace
+    Flt rv_d;
+};
+
+// trace lights shader sld ray depth recurs: set up frame 0.  Then call shm_step until it returns false; whenever it
+// returns true a query has been started in `q` and must be run to GS_DONE (qvm_step) before the next call.
+GD_FN void shm_start(SRegs& s, SHM& sh, int lightset, int sld, const Ray& ray, Flt depth, int recurs, TagArena* ta) {
+    s.L = 0; s.msp = 0; s.st = SS_T_BEGIN; s.fl = 0; s.m_id = -1; s.li = 0;
+    s.rv_c = mkca(0, 0, 0, 0); s.rv_d = GLM_INFINITY;
+    if (recurs > GS_MAX_RECURS) { recurs = GS_MAX_RECURS; s.fl |= GLOME_HITFLAG_CSG_OVERFLOW; }  // (the C-ABI rejects it earlier)
+    TFrame& T = sh.tf[0];
+    T.ray = ray; T.dlimit = depth; T.sld = sld; T.ls = lightset; T.recurs = recurs;
+    if (ta) { ta->n = 0; ta->overflow = 0; }
+}
+
 template <bool TAGS>
-GD_FN void gs_trace(const DScene& S, SHM& sh, int lightset, int sld, const Ray& ray, Flt depth, int recurs, ColorA& outc,
-                    GCnt& cnt, int& flags_out, TagArena* ta) {
+GD_FN bool shm_step(const DScene& S, SRegs& s, SHM& sh, QRegs& q, GCnt& cnt, TagArena* ta) {
     TFrame* tf = sh.tf;
     MFrame* mf = sh.mf;
-    int L = 0, msp = 0, st = SS_T_BEGIN, fl = 0;
-    ColorA rv_c = mkca(0, 0, 0, 0);
-    Flt rv_d = GLM_INFINITY;
+    int& L = s.L; int& msp = s.msp; int& st = s.st; int& fl = s.fl; int& m_id = s.m_id;
+    ColorA& rv_c = s.rv_c; Flt& rv_d = s.rv_d;
     MatVal m;
-    int m_id = -1;
     m.kind = -1; m.a = m.b = m.c = m.d = 0;
-    if (recurs > GS_MAX_RECURS) { recurs = GS_MAX_RECURS; fl |= GLOME_HITFLAG_CSG_OVERFLOW; }  // (the C-ABI rejects it earlier)
-    tf[0].ray = ray; tf[0].dlimit = depth; tf[0].sld = sld; tf[0].ls = lightset; tf[0].recurs = recurs;
-    if (TAGS) { ta->n = 0; ta->overflow = 0; }
 
 #define GS_CALL_TRACE(RAY, DLIM, REC, LS, SLD)                                                    \
     do {                                                                                          \
@@ -1225,7 +1347,11 @@ GD_FN void gs_trace(const DScene& S, SHM& sh, int lightset, int sld, const Ray& 
                 st = SS_T_RETURN;
                 continue;
             }
-            gq_query(S, sh.q, T.sld, T.ray, T.dlimit, false, cnt);
+            qvm_start(q, sh.q, T.sld, T.ray, T.dlimit, false);
+            st = SS_T_HIT;
+            return true;
+        }
+        if (st == SS_T_HIT) {  // rayint sld ray depth [] [] is in slot 0
             T.ri = sh.q.slot[0];
             fl |= T.ri.flags;
             if (!T.ri.hit) {  // mmissshade (Shader.hs:186)
@@ -1278,26 +1404,47 @@ GD_FN void gs_trace(const DScene& S, SHM& sh, int lightset, int sld, const Ray& 
             st = SS_M_EVAL;
             continue;
         }
+        if (st == SS_LIGHTS) {  // mpreshade (Shader.hs:65-80), one light per round; a shadow query may interrupt it
+            const Vec p = T.ri.pos, n = T.ri.norm;
+            bool asked = false;
+            while (s.li < T.L.count) {
+                Ray sr; Flt sd; bool ns = false;
+                if (!light_probe(S.lights + T.L.first + s.li, p, n, sr, sd, ns)) { s.li++; continue; }
+                if (ns) {
+                    cnt.shadow++;
+                    qvm_start(q, sh.q, T.sld, sr, sd, true);
+                    st = SS_LIGHT_RET;
+                    asked = true;
+                    break;
+                }
+                T.L.mask |= 1ull << s.li;
+                s.li++;
+            }
+            if (asked) return true;
+            T.L.done = 1;
+            mat_load(S, m_id, m);  // the Surface that forced ctxb
+            st = SS_M_EVAL;
+            continue;
+        }
+        if (st == SS_LIGHT_RET) {
+            fl |= sh.q.slot[0].flags;
+            if (!q.retb) T.L.mask |= 1ull << s.li;
+            s.li++;
+            st = SS_LIGHTS;
+            continue;
+        }
         if (st == SS_M_EVAL) {  // mpostshade (Shader.hs:82-184) of material m at the hit of frame L
             const Vec dir = T.ray.d, n = T.ri.norm, p = T.ri.pos;
             const Vec eyedir = vinvert(dir);
             switch (m.kind) {
                 case GLOME_MAT_SURFACE: {
-                    if (!T.L.done) {  // mpreshade (Shader.hs:65-80): forced by the first Surface that is shaded
-                        T.L.done = 1;
+                    if (!T.L.done) {  // ctxb is forced by the first Surface that is shaded (Trace.hs:63, Shader.hs:92)
                         T.L.first = S.lightsets[2 * T.ls];
                         T.L.count = S.lightsets[2 * T.ls + 1];
                         T.L.mask = 0;
-                        for (int li = 0; li < T.L.count; li++) {
-                            Ray sr; Flt sd; bool ns = false;
-                            if (!light_probe(S.lights + T.L.first + li, p, n, sr, sd, ns)) continue;
-                            if (ns) {
-                                cnt.shadow++;
-                                if (gq_query(S, sh.q, T.sld, sr, sd, true, cnt)) { fl |= sh.q.slot[0].flags; continue; }
-                                fl |= sh.q.slot[0].flags;
-                            }
-                            T.L.mask |= 1ull << li;
-                        }
+                        s.li = 0;
+                        st = SS_LIGHTS;
+                        break;
                     }
                     shade_surface(S, T.L, p, m.p, n, eyedir, rv_c);
                     st = SS_M_RET;
@@ -1446,14 +1593,27 @@ GD_FN void gs_trace(const DScene& S, SHM& sh, int lightset, int sld, const Ray& 
             continue;
         }
         // SS_T_RETURN: the trace of frame L is (rv_c, rv_d)
-        if (L == 0) break;
+        if (L == 0) { st = SS_FINISHED; return false; }
         L--;
         st = SS_M_RET;
     }
 #undef GS_CALL_TRACE
 #undef GS_MPUSH
-    outc = rv_c;
-    flags_out = fl;
+}
+
+// trace to completion (batch kernels, the pick query, the CPU harness): colour, the TraceResult's tag list when TAGS;
+// the primary Rayint is sh.tf[0].ri
+template <bool TAGS>
+GD_FN void gs_trace(const DScene& S, SHM& sh, int lightset, int sld, const Ray& ray, Flt depth, int recurs, ColorA& outc,
+                    GCnt& cnt, int& flags_out, TagArena* ta) {
+    SRegs s;
+    QRegs q;
+    shm_start(s, sh, lightset, sld, ray, depth, recurs, ta);
+    while (shm_step<TAGS>(S, s, sh, q, cnt, ta)) {
+        while (q.st != GS_DONE) qvm_step(S, q, sh.q, cnt);
+    }
+    outc = s.rv_c;
+    flags_out = s.fl;
 }
 
 // GHit -> the C-ABI's GlomeHit; tag ids go back through the scene's tag table

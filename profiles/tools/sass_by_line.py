@@ -30,7 +30,7 @@ for l in lines[start + 1:]:
     if m:
         loc = (m.group(1).split("/")[-1], int(m.group(2)))
         continue
-    if re.search(r"/\*[0-9a-f]{4}\*/\s+\S", l):
+    if re.search(r"/\*[0-9a-f]{4,}\*/\s+\S", l):
         insn_loc.append(loc)
 
 # --- ncu SASS rows for the first kernel instance in the csv whose name matches ---

@@ -16,7 +16,7 @@ using namespace ggen;
 
 struct HostScene {
     std::vector<GlomeNode> nodes;
-    std::vector<int32_t> ipool, tagvals, lightsets;
+    std::vector<int32_t> ipool, tagvals, lightsets, items;
     DScene d;
 };
 
@@ -51,7 +51,9 @@ void* genh_create(const GlomeFlatScene* fs) {
     if (!e.empty()) { delete h; return nullptr; }
     if (fs->n_lightsets > 0) h->lightsets.assign(fs->lightsets, fs->lightsets + 2 * fs->n_lightsets);
     else { h->lightsets.push_back(0); h->lightsets.push_back(fs->n_lights); }
+    glome_tagmap::build_items(h->nodes, h->items);
     memset(&h->d, 0, sizeof(h->d));
+    h->d.items = reinterpret_cast<const int4*>(h->items.data());
     h->d.nodes = h->nodes.data(); h->d.bih = fs->bihnodes; h->d.bvh = fs->bvhnodes; h->d.ipool = h->ipool.data();
     h->d.dpool = fs->dpool; h->d.textures = fs->textures; h->d.materials = fs->materials; h->d.lights = fs->lights;
     h->d.lightsets = h->lightsets.data(); h->d.tagvals = h->tagvals.data(); h->d.root = fs->root; h->d.n_lights = fs->n_lights;
