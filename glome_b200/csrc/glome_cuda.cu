@@ -391,6 +391,9 @@ __global__ void __launch_bounds__(128, 1) k_trace_samples(DScene S, TraceParams 
 // (per-lane refill, as the flat kernels do) is 2.7x SLOWER here (41 / 28 vs 15 / 8.4): the machine's rounds cost the sum
 // of the states present in the warp, and coherent neighbours stay in the same state while strangers do not.
 // ---------------------------------------------------------------------------------------------
+#ifndef GEN_BLOCK_SYNC
+#define GEN_BLOCK_SYNC 0
+#endif
 #ifndef GEN_SYNC_ROUNDS
 #define GEN_SYNC_ROUNDS 1  /* 1: the lanes of a warp start their queries together (warp-synchronous rounds) */
 #endif
@@ -407,11 +410,24 @@ __global__ void __launch_bounds__(GEN_THREADS, GEN_MINBLOCKS) k_gen_trace(DScene
     const long long total = (MODE == 0) ? (long long)P.n_sel * P.g.slots_per_tile : (long long)(*P.queue_count);
     const unsigned int chunk = (unsigned int)P.chunk;
     q.st = ggen::GS_DONE;
+#if GEN_BLOCK_SYNC
+    __shared__ unsigned int sbase;
+#endif
     for (;;) {
         unsigned int base = 0;
+#if GEN_BLOCK_SYNC
+        // the warps of a block take neighbouring micro-tiles at the same moment, so that they run the same parts of the
+        // machine's code at about the same time (instruction-cache locality across warps)
+        __syncthreads();
+        if (threadIdx.x == 0) sbase = atomicAdd(P.work_counter, chunk * (GEN_THREADS / 32));
+        __syncthreads();
+        base = sbase + (threadIdx.x >> 5) * chunk;
+        if ((long long)sbase >= total) break;
+#else
         if (lane == 0) base = atomicAdd(P.work_counter, chunk);
         base = __shfl_sync(FULL, base, 0);
         if ((long long)base >= total) break;
+#endif
         const long long w = (long long)base + lane;
         bool valid = w < total && lane < (int)chunk;
         int px = 0, py = 0;

@@ -329,7 +329,7 @@ enum {
     GF_BIH,         // bottom of a BIH's TRAV entries                           [hdr(previous BIH node)]
     GF_LIST,        // resume a list after a complex item                       [d ld hdr(next, end)]
     GF_CTX,         // restore the texture / tag context                        [tex.lo tex.hi tag.lo tag.hi hdr]
-    GF_INST,        // Instance (Solid.hs:386-403, 464-471)                     [o.xyz d.xyz d invlenscale 1/d.xyz hdr(node, parent slot)]
+    GF_INST,        // Instance (Solid.hs:386-403, 464-471)                     [o.xyz d.xyz d invlenscale 1/d.xyz cull hdr(node, parent slot)]
     GF_MODE,        // a rayint stood in for a shadow (Solid.hs:218-221)        [hdr(slot, previous acc)]
     GF_GATE,        // Bound (Bound.hs:30-49): shadow of the bounding object    [hdr(bounded node, previous mode)]
     GF_OR,          // InnerBound shadow (Bound.hs:101-103)                     [hdr(second node)]
@@ -420,8 +420,8 @@ struct SimpleHit { Flt t; Vec pos, norm; Ray ray; };
 // rayint / shadow of a simple item -- `{Tex,Tag}* prim` or `{..}* Instance ({..}* prim)` (Solid.hs:388-403) -- described by
 // its item record.  The ONE copy of the primitive tests in a kernel: the list loop and the CSG evaluators all call it.
 // (rx, ry, rz) = 1 / r.d of the caller's ray.  smode: only the hit flag is wanted (shadow).
-GD_NOINLINE bool gq_test_simple(const DScene& S, int4 it, Flt ox, Flt oy, Flt oz, Flt dx, Flt dy, Flt dz, Flt rx, Flt ry, Flt rz, Flt d,
-                                bool smode, SimpleHit* out, GCnt* cnt) {
+GD_FN bool gq_test_simple_inl(const DScene& S, int4 it, Flt ox, Flt oy, Flt oz, Flt dx, Flt dy, Flt dz, Flt rx, Flt ry, Flt rz, Flt d,
+                              bool smode, SimpleHit* out, GCnt* cnt) {
     const int cls = it.x & 15, ptype = (it.x >> 4) & 15;
     Ray tr = mkray(vec(ox, oy, oz), vec(dx, dy, dz));
     Flt td = d, invls = 1;
@@ -446,6 +446,12 @@ GD_NOINLINE bool gq_test_simple(const DScene& S, int4 it, Flt ox, Flt oy, Flt oz
     if (xfm) { out->t = t * invls; out->pos = xfm_point(xfm, pos); out->norm = vnorm(invxfm_norm(xfm, n)); }
     else { out->t = t; out->pos = pos; out->norm = n; }
     return true;
+}
+
+// the shared copy for the CSG evaluators
+GD_NOINLINE bool gq_test_simple(const DScene& S, int4 it, Flt ox, Flt oy, Flt oz, Flt dx, Flt dy, Flt dz, Flt rx, Flt ry, Flt rz, Flt d,
+                                bool smode, SimpleHit* out, GCnt* cnt) {
+    return gq_test_simple_inl(S, it, ox, oy, oz, dx, dy, dz, rx, ry, rz, d, smode, out, cnt);
 }
 
 // record a simple item's hit: the context stacks plus the item's own wrappers, outermost first (Tex.hs:54,66)
@@ -495,6 +501,7 @@ struct QRegs {
     bool shadow_q;          // the query: shadow (true) or rayint
     bool smode;             // current evaluation: shadow (any hit) or rayint (closest hit)
     bool retb;              // a shadow result travelling down the stack
+    bool cull;              // the current ray has unit length: best-hit culling and the origin clamp are safe (see qvm_start)
     int mflags;             // sticky overflow flags of this query
     int nadv;               // rayint_advance re-issues so far
     Ray r;
@@ -519,6 +526,14 @@ GD_FN void qvm_start(QRegs& q, QVM& vm, int root, const Ray& qray, Flt qd, bool 
     q.sp = 0; q.nslots = 1; q.acc = 0; q.acc_t = GLM_INFINITY; q.acc_hit = false;
     q.shadow_q = shadow_q; q.smode = shadow_q; q.retb = false; q.mflags = 0; q.nadv = 0;
     q.r = qray; q.d = qd;
+    // Best-hit culling and the origin clamp assume that a primitive's depth and a slab distance measure the
+    // same thing.  rayint_sphere (Sphere.hs:20-41) takes |d| = 1 for granted, and one ray of the reference is not
+    // normalised: Refract's refracted direction (Shader.hs:131-147).  For such a ray the walk follows the reference's own
+    // schedule: both children whenever their intervals allow, no clamp.  Below an Instance the ray is normalised again.
+    {
+        const Flt dd = vdot(qray.d, qray.d);
+        q.cull = (dd > 1 - 1e-12) && (dd < 1 + 1e-12);
+    }
     q.ctex = pstk_empty(); q.ctag = pstk_empty();
     q.cur_bih = -1; q.lin_ok = false;
     q.drx = 1 / qray.d.x; q.dry = 1 / qray.d.y; q.drz = 1 / qray.d.z;
@@ -535,7 +550,7 @@ GD_FN void qvm_step(const DScene& S, QRegs& q, QVM& vm, GCnt& cnt) {
     unsigned long long* cs = vm.cs;
     GHit* slot = vm.slot;
     int& sp = q.sp; int& nslots = q.nslots; int& acc = q.acc; Flt& acc_t = q.acc_t; bool& acc_hit = q.acc_hit;
-    bool& smode = q.smode; bool& retb = q.retb; int& mflags = q.mflags; int& nadv = q.nadv;
+    bool& smode = q.smode; bool& retb = q.retb; bool& cull = q.cull; int& mflags = q.mflags; int& nadv = q.nadv;
     Ray& r = q.r; Flt& d = q.d; PStk& ctex = q.ctex; PStk& ctag = q.ctag;
     int& cur_bih = q.cur_bih; bool& lin_ok = q.lin_ok; Flt& drx = q.drx; Flt& dry = q.dry; Flt& drz = q.drz;
     int& lin_j0 = q.lin_j0; int& lin_a0 = q.lin_a0; int& ref = q.ref; Flt& near_ = q.near_; Flt& far_ = q.far_;
@@ -574,7 +589,7 @@ GD_FN void qvm_step(const DScene& S, QRegs& q, QVM& vm, GCnt& cnt) {
         const Flt f1 = fmin_(dn, far_);
         bool v2 = df < far_;
         const Flt n2 = fmax_(df, near_);
-        if (!smode && v2 && acc_hit && n2 > acc_t) v2 = false;  // best-hit culling
+        if (!smode && cull && v2 && acc_hit && n2 > acc_t) v2 = false;  // best-hit culling
         if (v1 && v2) {
             GQ_NEED(3);
             cs[sp] = gq_d2w(far_); cs[sp + 1] = gq_d2w(n2);
@@ -617,7 +632,11 @@ GD_FN void qvm_step(const DScene& S, QRegs& q, QVM& vm, GCnt& cnt) {
             break;
         }
         SimpleHit sh_;
+#ifdef GQ_LIST_CALL
         if (!gq_test_simple(S, it, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, drx, dry, drz, ld, smode, &sh_, &cnt)) continue;
+#else
+        if (!gq_test_simple_inl(S, it, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, drx, dry, drz, ld, smode, &sh_, &cnt)) continue;
+#endif
         if (smode) { retb = true; st = GS_RET; continue; }
         if (acc_hit && acc_t < sh_.t) continue;
         gq_fill_hit(S, slot[acc], it, item, sh_, ctex, ctag, mflags);
@@ -655,7 +674,7 @@ GD_FN void qvm_step(const DScene& S, QRegs& q, QVM& vm, GCnt& cnt) {
                 Flt nr, fr;
                 bbclip_ub_pre(r, drx, dry, drz, bb, nr, fr);
                 fr = fmin_(d, fr);
-                if (nr < 0) nr = 0;  // origin clamp
+                if (cull && nr < 0) nr = 0;  // origin clamp
                 if (nd.a >= 0 && nr > fr) { st = GS_RET; break; }  // Bih.hs:347 at the root
                 GQ_NEED(1);
                 cs[sp++] = gq_hdr(GF_BIH, cur_bih, 0);
@@ -697,13 +716,15 @@ GD_FN void qvm_step(const DScene& S, QRegs& q, QVM& vm, GCnt& cnt) {
                 const Vec neworig = invxfm_point(xfm, r.o);
                 const Flt lenscale = vlen(newdir);
                 const Flt invls = 1 / lenscale;
-                GQ_NEED(12);
+                GQ_NEED(13);
                 cs[sp] = gq_d2w(r.o.x); cs[sp + 1] = gq_d2w(r.o.y); cs[sp + 2] = gq_d2w(r.o.z);
                 cs[sp + 3] = gq_d2w(r.d.x); cs[sp + 4] = gq_d2w(r.d.y); cs[sp + 5] = gq_d2w(r.d.z);
                 cs[sp + 6] = gq_d2w(d); cs[sp + 7] = gq_d2w(invls);
                 cs[sp + 8] = gq_d2w(drx); cs[sp + 9] = gq_d2w(dry); cs[sp + 10] = gq_d2w(drz);
-                cs[sp + 11] = gq_hdr(GF_INST, ni, acc);
-                sp += 12;
+                cs[sp + 11] = cull ? 1ull : 0ull;
+                cs[sp + 12] = gq_hdr(GF_INST, ni, acc);
+                sp += 13;
+                cull = true;  // the object-space ray is normalised (Solid.hs:392)
                 if (!smode) {
                     GQ_NEED_SLOT(1);
                     ghit_clear(slot[nslots]);
@@ -791,7 +812,7 @@ GD_FN void qvm_step(const DScene& S, QRegs& q, QVM& vm, GCnt& cnt) {
                 sp -= 2;
                 if (smode && retb) break;  // an occluder was found: drop the pending subtrees
                 const Flt nn = gq_w2d(cs[sp + 1]);
-                if (!smode && acc_hit && nn > acc_t) break;  // best-hit culling
+                if (!smode && cull && acc_hit && nn > acc_t) break;  // best-hit culling
                 ref = (int)(unsigned int)(h >> 32);
                 near_ = nn;
                 far_ = gq_w2d(cs[sp]);
@@ -822,12 +843,13 @@ GD_FN void qvm_step(const DScene& S, QRegs& q, QVM& vm, GCnt& cnt) {
                 ctex.lo = cs[sp]; ctex.hi = cs[sp + 1]; ctag.lo = cs[sp + 2]; ctag.hi = cs[sp + 3];
                 break;
             case GF_INST: {
-                sp -= 11;
+                sp -= 12;
                 const int node = gq_a(h), parent = gq_b(h);
                 r.o = vec(gq_w2d(cs[sp]), gq_w2d(cs[sp + 1]), gq_w2d(cs[sp + 2]));
                 r.d = vec(gq_w2d(cs[sp + 3]), gq_w2d(cs[sp + 4]), gq_w2d(cs[sp + 5]));
                 d = gq_w2d(cs[sp + 6]);
                 drx = gq_w2d(cs[sp + 8]); dry = gq_w2d(cs[sp + 9]); drz = gq_w2d(cs[sp + 10]);
+                cull = cs[sp + 11] != 0;
                 if (smode) break;
                 const Flt invls = gq_w2d(cs[sp + 7]);
                 const GHit& c = slot[acc];
@@ -1272,7 +1294,7 @@ GD_NOINLINE int gq_debug_count(const DScene& S, QVM& vm, int root, const Ray& ra
 #define GS_MAX_RECURS 8                  /* `recurs` accepted by the general tracer */
 #define GS_TFRAMES (GS_MAX_RECURS + 1)
 #define GS_MFRAMES 24
-#define GS_TAGCAP 64
+#define GS_TAGCAP 512 /* the pick query only: one thread, so the arena can be generous */
 
 struct TFrame {
     Ray ray;

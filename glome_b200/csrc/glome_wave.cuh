@@ -212,8 +212,10 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScen
     __shared__ int g_item[ANY ? 1 : GW_THREADS], g_pend[ANY ? 1 : GW_THREADS], g_ovf[ANY ? 1 : GW_THREADS];
     __shared__ long long g_s[ANY ? 1 : GW_THREADS];
     __shared__ unsigned long long g_cull[ANY ? 1 : GW_THREADS];  // bits of the group's nearest depth so far (culling only)
+    __shared__ int g_tie[ANY ? 1 : GW_THREADS];  // two members brought different items at exactly the same depth
     const int gb = threadIdx.x & ~31;
     if (!ANY) light = -1;
+    bool solo = false;               // closest: this lane re-walks a ray alone (after a tie) and must not donate
 #endif
 
     for (;;) {
@@ -290,8 +292,11 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScen
         // 1/N of a frame per GPU).  A ray's pushed subtrees are independent given (ray, near, far), so a
         // busy lane donates the oldest entry of its stack (the subtree nearest the root) to an idle lane
         // of its warp, which traverses it with the donor's ray.  Every leaf still sees the (ray, far) of
-        // the sequential walk, so the union of the partial results is the sequential result (two distinct
-        // primitives at exactly the same depth could resolve differently; none does in any test scene).
+        // the sequential walk, so the union of the partial results is the sequential result -- except for the
+        // reference's tie rule (`nearest`: of two hits at exactly the same depth the one met LATER by the sequential
+        // walk wins, Solid.hs:37-44, Bih.hs:350-366): members finish in any order.  So the fold only NOTES a tie
+        // between different items; the lane that completes such a group walks the ray once more, alone and in
+        // order (solo), and that result is the one written.
         // members of a group share their nearest depth every round, so that a subtree behind a neighbour's hit is culled
         if (!ANY && nomore && active && light >= 0) {
             if (has) atomicMin(&g_cull[gb + light], (unsigned long long)__double_as_longlong(best_t));
@@ -306,12 +311,30 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScen
                     fin &= fin - 1;
                     if (lane == l) {
                         const int g = gb + light;
+                        if (best_item >= 0 && g_item[g] >= 0 && g_item[g] != best_item && g_t[g] == best_t) g_tie[g] = 1;
                         if (best_item >= 0 && (g_item[g] < 0 || !(g_t[g] < best_t))) { g_t[g] = best_t; g_item[g] = best_item; }
                         g_ovf[g] |= (int)n_ovf;
                         n_ovf = 0;
                         const int left = g_pend[g] - 1;
                         g_pend[g] = left;
-                        if (left == 0) {
+                        if (left == 0 && g_tie[g]) {
+                            // the order of arrival decided between equal depths: redo this ray sequentially
+                            // (every member carries the group's ray, dmax and sample)
+                            s = g_s[g];
+                            if (segidx > 0) {
+                                best_seg = P.hit_seg[s];
+                                has = best_seg >= 0;
+                                best_t = has ? P.hit_t[s] : (Flt)GLM_INFINITY;
+                            } else { has = false; best_t = GLM_INFINITY; best_seg = -1; }
+                            best_item = -1;
+                            bbclip_ub(r, bb, near_, far_);
+                            far_ = fmin_(dmax, far_);
+                            if (near_ < 0) near_ = 0;
+                            ref = bn.a; sp = 0; sb = 0;
+                            n_ovf = (unsigned int)(g_ovf[g] != 0);
+                            solo = true;
+                            active = true;
+                        } else if (left == 0) {
                             const long long ss = g_s[g];
                             const bool found = g_item[g] >= 0;
                             if (found) { P.hit_t[ss] = g_t[g]; P.hit_seg[ss] = segidx; P.hit_item[ss] = g_item[g]; P.hit_sub[ss] = -1; }
@@ -332,7 +355,7 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScen
             // hit that culls its pending subtrees, so walking those in parallel is wasted work).  Measured on B200: the
             // greedy setting (0) does up to 2x the node visits on small waves and is still the fastest (720x480 AA:
             // 4.26 ms vs 4.70 ms at 128 and 5.26 ms at 256), because those waves are latency-bound, not issue-bound.
-            const bool can_give = active && sp > sb && (GW_STEAL_AFTER == 0 || (n_bih - n_start) >= GW_STEAL_AFTER);
+            const bool can_give = active && !solo && sp > sb && (GW_STEAL_AFTER == 0 || (n_bih - n_start) >= GW_STEAL_AFTER);
             const unsigned int donors = __ballot_sync(FULL, can_give);
             const int np = min(__popc(free_), __popc(donors));
             if (np > 0) {
@@ -348,6 +371,7 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScen
                         if (light < 0) {  // first donation: this lane becomes the root of a group
                             light = lane;
                             g_t[gb + lane] = GLM_INFINITY; g_item[gb + lane] = -1; g_ovf[gb + lane] = 0; g_s[gb + lane] = s;
+                            g_tie[gb + lane] = 0;
                             g_pend[gb + lane] = 1;
                             g_cull[gb + lane] = (unsigned long long)__double_as_longlong(has ? best_t : (Flt)GLM_INFINITY);
                         }
@@ -498,6 +522,9 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScen
                 if (segidx == 0) P.hit_flags[s] = n_ovf ? GLOME_HITFLAG_STACK_OVERFLOW : 0;
                 else if (n_ovf) P.hit_flags[s] |= GLOME_HITFLAG_STACK_OVERFLOW;
                 n_ovf = 0;
+#if GW_STEAL
+                solo = false;
+#endif
             }
             active = false;
         }

@@ -1082,8 +1082,8 @@ static inline Mat mat_from_table(const Scene& S, int id) {
     return r;
 }
 struct TraceResult { ColorA c; List tags; Rayint ri; };
-struct LightCtx {  // ctxb = [(Color, Vec)], forced lazily (Trace.hs:63)
-    bool done; int n; Color col[16]; Vec dir[16];
+struct LightCtx {  // ctxb = [(Color, Vec)], forced lazily (Trace.hs:63); a list: any number of lights
+    bool done; int n; std::vector<Color> col; std::vector<Vec> dir;
 };
 
 static TraceResult trace(const Scene& S, int lightset, int sld, const Ray& ray, Flt depth, int recurs);
@@ -1092,6 +1092,7 @@ static void mpreshade(const Scene& S, int lightset, const Ray& ray, int scene, c
     // Shader.hs:65-80
     (void)ray;
     ctx.done = true; ctx.n = 0;
+    ctx.col.clear(); ctx.dir.clear();
     if (!ri.hit) return;
     int first = S.lightsets[2 * lightset], cnt = S.lightsets[2 * lightset + 1];
     for (int li = 0; li < cnt; li++) {
@@ -1110,7 +1111,7 @@ static void mpreshade(const Scene& S, int lightset, const Ray& ray, int scene, c
         if (blocked) continue;
         Flt fall = 1 / (llen * llen);  // Shader.hs:23
         Color lc = {L.color[0], L.color[1], L.color[2]};
-        if (ctx.n < 16) { ctx.col[ctx.n] = cscale(lc, fall); ctx.dir[ctx.n] = ldir; ctx.n++; }
+        ctx.col.push_back(cscale(lc, fall)); ctx.dir.push_back(ldir); ctx.n++;
     }
 }
 

@@ -108,7 +108,7 @@ void genh_trace_batch(void* hp, int64_t n, const double* rays, const double* tma
         if (hits) { ghit_out(h->d, sh.tf[0].ri, hits + i); hits[i].flags |= fl; }
         if (tags) {
             int32_t* o = tags + 17 * i;
-            o[0] = ta.n;
+            o[0] = ta.n < 16 ? ta.n : 16;  // (the oracle's list is capped at 16 entries)
             for (int k = 0; k < 16; k++) o[1 + k] = k < ta.n ? h->d.tagvals[ta.v[k]] : -1;
         }
         nshadow += c.shadow; nsec += c.secondary; ncsg += c.csg; nbih += c.bih; nprim += c.prim; ninst += c.inst;
