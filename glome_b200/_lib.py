@@ -176,6 +176,7 @@ SIGNATURES = {
     "glome_camera": (C.c_int, [_dp, _dp, _dp, C.c_double, _P(GlomeCamera)]),
     "glome_sb_flatten": (C.c_int, [_vp, C.c_int, _P(GlomeFlatScene)]),
     "glome_sb_config_scene": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_uint64, _P(GlomeCamera), _ip]),
+    "glome_stdgen_probe": (C.c_int, [C.c_int64, _P(C.c_uint64), _dp, _P(C.c_uint64)]),
     "glome_sb_load_nff": (C.c_int, [_vp, C.c_char_p, C.c_int64, _P(GlomeCamera), _dp, _P(C.c_int64)]),
     "glome_bih_build": (C.c_int, [C.c_int64, _vp, _P(_P(GlomeBihNode)), _ip, _P(_ip), _ip, _P(_ip), _ip, _dp]),
     "glome_bih_build_gpu": (C.c_int, [C.c_int64, _vp, C.c_int, _P(_P(GlomeBihNode)), _ip, _P(_ip), _ip, _P(_ip), _ip, _dp, _dp]),

@@ -15,6 +15,15 @@ void glome_set_error(const std::string& s);  // glome_cuda.cu
 
 struct GlomeBuilder { Builder b; };
 
+namespace glome_host {  // scenes.cpp: the StdGen of random-1.2 (TestScene's oak)
+struct StdGen { uint64_t seed, gamma; };
+StdGen mkStdGen(int64_t n);
+uint64_t stdgen_next_word64(StdGen& g);
+void stdgen_split(const StdGen& g, StdGen& a, StdGen& b);
+double stdgen_randomR_double(double l, double h, StdGen& g);
+uint64_t splitmix64_vigna(uint64_t& x);
+}
+
 #define GUARD(expr)                                          \
     try { return (expr); }                                   \
     catch (const BuildError& e) { glome_set_error(e.msg); return GLOME_EBUILD; } \
@@ -25,6 +34,25 @@ static inline Xfm X(const double* p) { Xfm x; memcpy(x.m, p, sizeof(x.m)); retur
 static std::vector<int32_t> IV(int n, const int32_t* p) { return std::vector<int32_t>(p, p + (n > 0 ? n : 0)); }
 
 extern "C" {
+
+// System.Random (random-1.2) as restated for TestScene's oak: out = {seed, gamma of mkStdGen n; the next three Word64 of
+// that generator; seed, gamma of both halves of `split`}; dout = three successive `randomR (0, 0.5)` on mkStdGen n;
+// vigna = the first output of Vigna's splitmix64 started at x = n (a published known answer for the mixing function).
+int glome_stdgen_probe(int64_t n, uint64_t out[9], double dout[3], uint64_t* vigna) {
+    if (!out || !dout || !vigna) return GLOME_EINVAL;
+    StdGen g = mkStdGen(n);
+    out[0] = g.seed; out[1] = g.gamma;
+    StdGen h = g;
+    for (int i = 0; i < 3; i++) out[2 + i] = stdgen_next_word64(h);
+    StdGen a, b;
+    stdgen_split(g, a, b);
+    out[5] = a.seed; out[6] = a.gamma; out[7] = b.seed; out[8] = b.gamma;
+    StdGen d = g;
+    for (int i = 0; i < 3; i++) dout[i] = stdgen_randomR_double(0, 0.5, d);
+    uint64_t x = (uint64_t)n;
+    *vigna = splitmix64_vigna(x);
+    return GLOME_OK;
+}
 
 int glome_builder_create(GlomeBuilder** out) {
     if (!out) return GLOME_EINVAL;

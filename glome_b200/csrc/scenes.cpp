@@ -88,16 +88,57 @@ static int lattice(Builder& b) {  // TestScene.hs:21-25
     return b.bih(xs);
 }
 
-// oak (TestScene.hs:68-110).  The reference draws branch parameters from System.Random's StdGen
-// (mkStdGen 42, split, randomR); the `random` package version is unpinned in GlomeView.cabal:26 and
-// its generator changed between releases, so the exact stream cannot be reproduced: PARITY
-// UNPINNED for this sub-object.  Substitute: splitmix64, `split` = two hashed child seeds.
-struct OakRng { uint64_t s; };
-static void oak_split(const OakRng& r, OakRng& a, OakRng& c) {
-    uint64_t s = r.s;
-    a.s = splitmix64(s);
-    c.s = splitmix64(s);
+// oak (TestScene.hs:68-110).  The reference draws the branch parameters from System.Random's StdGen: `mkStdGen 42`,
+// `split`, `randomR` (TestScene.hs:83-88, 190).  GlomeView.cabal:26 leaves the `random` version open; every GHC install of
+// the last years resolves it to random >= 1.2, whose StdGen is splitmix's SMGen.  Restated here from the published
+// algorithm (PINNED ASSUMPTION: random-1.2.1 with splitmix-0.1.x; the sources are not in this image, so this sub-object
+// stays "parity unpinned" until bench/GlomeHeadless.hs prints the same first draws on a GHC box):
+//   SMGen seed gamma;  mkSMGen s = SMGen (mix64 s) (mixGamma (s + goldenGamma))          (System.Random.SplitMix)
+//   nextWord64 (SMGen s g) = (mix64 (s + g), SMGen (s + g) g)
+//   splitSMGen (SMGen s g) = (SMGen s'' g, SMGen (mix64 s') (mixGamma s''))   with s' = s + g, s'' = s' + g
+//   randomR (l, h) :: Double = x * l + (1 - x) * h,  x = fromIntegral w64 / fromIntegral (maxBound :: Word64)
+//                                                                       (System.Random.Internal: uniformRM, uniformDouble01M)
+struct StdGen { uint64_t seed, gamma; };
+static inline uint64_t sm_shift_xor(int n, uint64_t w) { return w ^ (w >> n); }
+static inline uint64_t sm_mix64(uint64_t z) {  // MurmurHash3's finaliser, as in java.util.SplittableRandom
+    z = sm_shift_xor(33, z) * 0xff51afd7ed558ccdULL;
+    z = sm_shift_xor(33, z) * 0xc4ceb9fe1a85ec53ULL;
+    return sm_shift_xor(33, z);
 }
+static inline uint64_t sm_mix64variant13(uint64_t z) {  // Stafford's variant 13 (Vigna's splitmix64 output function)
+    z = sm_shift_xor(30, z) * 0xbf58476d1ce4e5b9ULL;
+    z = sm_shift_xor(27, z) * 0x94d049bb133111ebULL;
+    return sm_shift_xor(31, z);
+}
+static inline uint64_t sm_mix_gamma(uint64_t z) {
+    uint64_t g = sm_mix64variant13(z) | 1ULL;
+    int n = __builtin_popcountll(g ^ (g >> 1));
+    return n >= 24 ? g : g ^ 0xaaaaaaaaaaaaaaaaULL;
+}
+static const uint64_t SM_GOLDEN_GAMMA = 0x9e3779b97f4a7c15ULL;
+StdGen mkStdGen(int64_t n) {
+    uint64_t s = (uint64_t)n;
+    StdGen g = {sm_mix64(s), sm_mix_gamma(s + SM_GOLDEN_GAMMA)};
+    return g;
+}
+uint64_t stdgen_next_word64(StdGen& g) {
+    g.seed += g.gamma;
+    return sm_mix64(g.seed);
+}
+void stdgen_split(const StdGen& g, StdGen& a, StdGen& b) {
+    uint64_t s1 = g.seed + g.gamma, s2 = s1 + g.gamma;
+    a.seed = s2; a.gamma = g.gamma;
+    b.seed = sm_mix64(s1); b.gamma = sm_mix_gamma(s2);
+}
+double stdgen_randomR_double(double l, double h, StdGen& g) {
+    if (l == h) return l;
+    double x = (double)stdgen_next_word64(g) / 18446744073709551615.0;  // fromIntegral w64 / fromIntegral (maxBound :: Word64)
+    return x * l + (1 - x) * h;
+}
+uint64_t splitmix64_vigna(uint64_t& x) { return sm_mix64variant13(x += SM_GOLDEN_GAMMA); }  // known-answer hook (tests)
+
+typedef StdGen OakRng;
+static void oak_split(const OakRng& r, OakRng& a, OakRng& c) { stdgen_split(r, a, c); }
 static int oak_tree(Builder& b, int n_, OakRng r, Flt season, int t_leaf) {
     const Flt thickness = 0.03;
     const Flt minbranch = deg(10), maxbranch = deg(25);
@@ -108,11 +149,11 @@ static int oak_tree(Builder& b, int n_, OakRng r, Flt season, int t_leaf) {
     OakRng rng1, rng2, rng3, rng4;
     oak_split(r, rng1, rng2);
     oak_split(rng1, rng3, rng4);
-    uint64_t s = rng4.s;
-    Flt r1 = urange(s, 0, 0.5);
-    Flt r2 = urange(s, minbranch, maxbranch);
-    Flt r3 = urange(s, 0.8, 0.95);
-    (void)u01(s);  // r4 is compared with (1 :: Float) and never exceeds it (TestScene.hs:92-94)
+    OakRng rng5 = rng4;  // (r1,rng5) = randomR (0,0.5) rng4 ... : one generator threaded through the three draws
+    Flt r1 = stdgen_randomR_double(0, 0.5, rng5);
+    Flt r2 = stdgen_randomR_double(minbranch, maxbranch, rng5);
+    Flt r3 = stdgen_randomR_double(0.8, 0.95, rng5);
+    // r4 :: Float in (0,1) is compared with 1 and never exceeds it (TestScene.hs:87,92-94): it selects nothing
     Flt seglen = 0.5 + r1, branchang = r2, scaling = r3;
     int n = n_;
     std::vector<int32_t> parts;
@@ -132,8 +173,7 @@ static int oak(Builder& b, Flt age, uint64_t seed) {
     int year = (int)floor(age);
     Flt season = age - (Flt)year;
     int t_leaf = t_matte(b, 0.2, 1, 0.4);
-    OakRng r;
-    r.s = seed;
+    OakRng r = mkStdGen((int64_t)seed);  // oak 11.4 (mkStdGen 42)  (TestScene.hs:190)
     int tree = oak_tree(b, year, r, season, t_leaf);
     // bih (tolist (SolidItem (flatten_transform (tree year rng))))
     std::vector<int32_t> leaves = b.tolist(b.list_raw(b.flatten_transform(tree)));

@@ -414,6 +414,12 @@ int glome_sb_flatten(GlomeBuilder* b, int root, GlomeFlatScene* out);
 int glome_sb_config_scene(GlomeBuilder* b, int config, int64_t n, uint64_t seed, GlomeCamera* cam,
                           int* recurs_out);
 
+/* TestScene's oak draws from System.Random's StdGen (TestScene.hs:83-88,190).  Probe of the restated generator
+ * (random-1.2 / splitmix, glome_b200/csrc/scenes.cpp) for known-answer tests and for comparison with a GHC run:
+ * out = {seed, gamma of `mkStdGen n`; its next three Word64; seed, gamma of both halves of `split`},
+ * dout = three successive `randomR (0, 0.5) :: Double`, vigna = first output of Vigna's splitmix64 from x = n. */
+int glome_stdgen_probe(int64_t n, uint64_t out[9], double dout[3], uint64_t* vigna);
+
 /* NFF (Neutral File Format, the SPD benchmark scenes) reader: Spd.hs:1-261, quirks included (groups and lights end
  * up in reverse file order, the last camera / background win, a "#" comment ends the scene; see nff.cpp).
  * Adds the scene's items, materials and lights to the builder and returns the root item
