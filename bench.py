@@ -179,6 +179,7 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    os.environ["GLOME_HOST_ONLY"] = "1"  # scene construction only: this arm never maps the CUDA library
     import glome_b200 as G
     threads = os.cpu_count() or 1
     cfg = args.config

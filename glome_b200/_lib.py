@@ -10,6 +10,10 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GLOME_LIB") or os.path.join(_HERE, "_build", "libglomecuda.so")  # GLOME_LIB: A/B builds
+# libglomehost.so: scene construction only (the host mirror of the GlomeTrace constructors, tree builders, NFF reader); no
+# CUDA in it.  GLOME_HOST_ONLY=1 makes load() hand out this library alone -- what bench.py's CPU reference arm does, so
+# that the arm never maps the CUDA library.
+HOST_LIB_PATH = os.path.join(os.path.dirname(LIB_PATH), "libglomehost.so")
 
 GLOME_MAX_STACK = 8
 
@@ -201,12 +205,18 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise ImportError("libglomecuda.so not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
-                          "(expected at %s); there is no CPU fallback" % LIB_PATH)
-    lib = C.CDLL(LIB_PATH)
+    host_only = os.environ.get("GLOME_HOST_ONLY") == "1"
+    path = HOST_LIB_PATH if host_only else LIB_PATH
+    if not os.path.exists(path):
+        raise ImportError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(expected at %s); there is no CPU fallback" % (os.path.basename(path), path))
+    lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
-        fn = getattr(lib, name)
+        fn = getattr(lib, name, None)
+        if fn is None:
+            if host_only:
+                continue  # a device entry point: absent from the host library by construction
+            raise ImportError("libglomecuda.so does not export %s" % name)
         fn.restype = res
         fn.argtypes = args
     _lib = lib

@@ -24,10 +24,14 @@ double stdgen_randomR_double(double l, double h, StdGen& g);
 uint64_t splitmix64_vigna(uint64_t& x);
 }
 
-#define GUARD(expr)                                          \
-    try { return (expr); }                                   \
-    catch (const BuildError& e) { glome_set_error(e.msg); return GLOME_EBUILD; } \
-    catch (const std::exception& e) { glome_set_error(e.what()); return GLOME_EBUILD; }
+// no exception crosses the C boundary (a Haskell or ctypes caller would be terminated by it)
+#define GUARD_CATCH                                                                          \
+    catch (const BuildError& e) { glome_set_error(e.msg); return GLOME_EBUILD; }              \
+    catch (const std::exception& e) { glome_set_error(e.what()); return GLOME_EBUILD; }       \
+    catch (...) { glome_set_error("unknown exception"); return GLOME_EBUILD; }
+#define GUARD(expr)        \
+    try { return (expr); } \
+    GUARD_CATCH
 
 static inline Vec V(const double* p) { return vec(p[0], p[1], p[2]); }
 static inline Xfm X(const double* p) { Xfm x; memcpy(x.m, p, sizeof(x.m)); return x; }
@@ -78,7 +82,7 @@ int glome_sb_spheres(GlomeBuilder* b, int64_t n, const double* centers, const do
         b->b.items.reserve(b->b.items.size() + (size_t)n);
         for (int64_t i = 0; i < n; i++) ids_out[i] = b->b.sphere(V(centers + 3 * i), radii[i]);
         return GLOME_OK;
-    } catch (const BuildError& e) { glome_set_error(e.msg); return GLOME_EBUILD; }
+    } GUARD_CATCH
 }
 int glome_sb_triangle(GlomeBuilder* b, const double p[9]) { GUARD(b->b.triangle(V(p), V(p + 3), V(p + 6))); }
 int glome_sb_trianglenorm(GlomeBuilder* b, const double p[18]) {
@@ -113,19 +117,19 @@ int glome_sb_transform(GlomeBuilder* b, int item, int nx, const double* xfms) {
         std::vector<Xfm> xs;
         for (int i = 0; i < nx; i++) xs.push_back(X(xfms + 24 * i));
         return b->b.transform(item, xs);
-    } catch (const BuildError& e) { glome_set_error(e.msg); return GLOME_EBUILD; }
+    } GUARD_CATCH
 }
 int glome_xfm_translate(const double v[3], double out[24]) {
     try { Xfm x = translate(V(v)); memcpy(out, x.m, sizeof(x.m)); return GLOME_OK; }
-    catch (const BuildError& e) { glome_set_error(e.msg); return GLOME_EBUILD; }
+    GUARD_CATCH
 }
 int glome_xfm_scale(const double v[3], double out[24]) {
     try { Xfm x = scale(V(v)); memcpy(out, x.m, sizeof(x.m)); return GLOME_OK; }
-    catch (const BuildError& e) { glome_set_error(e.msg); return GLOME_EBUILD; }
+    GUARD_CATCH
 }
 int glome_xfm_rotate(const double axis[3], double angle, double out[24]) {
     try { Xfm x = rotate(V(axis), angle); memcpy(out, x.m, sizeof(x.m)); return GLOME_OK; }
-    catch (const BuildError& e) { glome_set_error(e.msg); return GLOME_EBUILD; }
+    GUARD_CATCH
 }
 int glome_xfm_compose(int n, const double* xfms, double out[24]) {
     try {
@@ -134,20 +138,20 @@ int glome_xfm_compose(int n, const double* xfms, double out[24]) {
         Xfm x = compose(xs);
         memcpy(out, x.m, sizeof(x.m));
         return GLOME_OK;
-    } catch (const BuildError& e) { glome_set_error(e.msg); return GLOME_EBUILD; }
+    } GUARD_CATCH
 }
 int glome_sb_flatten_transform_bih(GlomeBuilder* b, int item) {
     try {
         std::vector<int32_t> leaves = b->b.tolist(b->b.list_raw(b->b.flatten_transform(item)));
         return b->b.bih(leaves);
-    } catch (const BuildError& e) { glome_set_error(e.msg); return GLOME_EBUILD; }
+    } GUARD_CATCH
 }
 int glome_sb_bound(GlomeBuilder* b, int item, double out[6]) {
     try {
         glm::Bbox bb = b->b.bound(item);
         out[0] = bb.p1.x; out[1] = bb.p1.y; out[2] = bb.p1.z; out[3] = bb.p2.x; out[4] = bb.p2.y; out[5] = bb.p2.z;
         return GLOME_OK;
-    } catch (const BuildError& e) { glome_set_error(e.msg); return GLOME_EBUILD; }
+    } GUARD_CATCH
 }
 
 int glome_sb_mat_surface(GlomeBuilder* b, const double rgb[3], double alpha, double amb, double kd, double ks, double shine) {
@@ -183,7 +187,7 @@ int glome_camera(const double pos[3], const double at[3], const double up[3], do
 
 int glome_sb_flatten(GlomeBuilder* b, int root, GlomeFlatScene* out) {
     try { b->b.flatten(root, out); return GLOME_OK; }
-    catch (const BuildError& e) { glome_set_error(e.msg); return GLOME_EBUILD; }
+    GUARD_CATCH
 }
 
 int glome_sb_config_scene(GlomeBuilder* b, int config, int64_t n, uint64_t seed, GlomeCamera* cam, int* recurs_out) {
@@ -226,7 +230,7 @@ static int bih_build_any(int64_t n, const double* bboxes, int device, double* ti
         bb_out[0] = t.bb.p1.x; bb_out[1] = t.bb.p1.y; bb_out[2] = t.bb.p1.z;
         bb_out[3] = t.bb.p2.x; bb_out[4] = t.bb.p2.y; bb_out[5] = t.bb.p2.z;
         return GLOME_OK;
-    } catch (const BuildError& e) { glome_set_error(e.msg); return GLOME_EBUILD; }
+    } GUARD_CATCH
 }
 static int mesh_build_any(int64_t nverts, const double* verts, int64_t ntris, const int32_t* tris, int device, double* timings_ms,
                           GlomeBvhNode** nodes_out, int32_t* n_nodes_out, int32_t** leafpool_out, int32_t* n_leafpool_out,
@@ -265,7 +269,7 @@ static int mesh_build_any(int64_t nverts, const double* verts, int64_t ntris, co
         bb_out[0] = t.bb.p1.x; bb_out[1] = t.bb.p1.y; bb_out[2] = t.bb.p1.z;
         bb_out[3] = t.bb.p2.x; bb_out[4] = t.bb.p2.y; bb_out[5] = t.bb.p2.z;
         return GLOME_OK;
-    } catch (const BuildError& e) { glome_set_error(e.msg); return GLOME_EBUILD; }
+    } GUARD_CATCH
 }
 void glome_free(void* p) { free(p); }
 

@@ -648,7 +648,7 @@ static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
 }  // namespace
 
-void bih_build_gpu(int64_t n64, const double* bboxes, int device, BihTree& out, double* timings_ms) {
+static void bih_build_gpu_impl(int64_t n64, const double* bboxes, int device, BihTree& out, double* timings_ms) {
     if (n64 < 0 || n64 > 0x3fffffff) throw BuildError("bih_build_gpu: item count out of range");
     const int n = (int)n64;
     int ndev = 0;
@@ -766,7 +766,7 @@ void bih_build_gpu(int64_t n64, const double* bboxes, int device, BihTree& out, 
     }
 }
 
-void mesh_build_gpu(int64_t nverts64, const double* verts, int64_t ntris64, const int32_t* tris, int device, MeshTree& out,
+static void mesh_build_gpu_impl(int64_t nverts64, const double* verts, int64_t ntris64, const int32_t* tris, int device, MeshTree& out,
                     double* timings_ms) {
     if (ntris64 < 0 || ntris64 > 0x3fffffff || nverts64 < 0 || nverts64 > 0x3fffffff) throw BuildError("mesh_build_gpu: size out of range");
     if (ntris64 == 0 || nverts64 == 0) {  // nothing to sweep
@@ -882,5 +882,14 @@ void mesh_build_gpu(int64_t nverts64, const double* verts, int64_t ntris64, cons
         timings_ms[0] = a; timings_ms[1] = b; timings_ms[2] = c;
     }
 }
+
+// libglomecuda.so hands its builders to libglomehost.so when it is loaded (host_base.cpp)
+extern void (*hook_bih_build_gpu)(int64_t, const double*, int, BihTree&, double*);
+extern void (*hook_mesh_build_gpu)(int64_t, const double*, int64_t, const int32_t*, int, MeshTree&, double*);
+namespace {
+struct RegisterGpuBuilders {
+    RegisterGpuBuilders() { hook_bih_build_gpu = &bih_build_gpu_impl; hook_mesh_build_gpu = &mesh_build_gpu_impl; }
+} g_register_gpu_builders;
+}  // namespace
 
 }  // namespace glome_host

@@ -39,9 +39,8 @@ using namespace gdev;
 // ---------------------------------------------------------------------------------------------
 // error plumbing
 // ---------------------------------------------------------------------------------------------
-static thread_local std::string g_err;
-extern "C" const char* glome_last_error(void) { return g_err.c_str(); }
-void glome_set_error(const std::string& s) { g_err = s; }
+std::string& glome_err_ref();  // host_base.cpp (libglomehost.so): the C-ABI's thread-local error string
+#define g_err (glome_err_ref())
 
 #define CK(call)                                                                                   \
     do {                                                                                           \
@@ -1182,32 +1181,6 @@ extern "C" int glome_debug_count_batch(GlomeScene* s, int64_t n, const double* r
     return GLOME_OK;
 }
 
-extern "C" void glome_render_opts_default(GlomeRenderOpts* o) {
-    memset(o, 0, sizeof(*o));
-    o->mode = GLOME_MODE_ADAPTIVE_AA;  // the live path of the reference (Glome.hs:385)
-    o->blocksize = 65;                 // Glome.hs:116
-    o->recurs = 3;                     // Glome.hs:25
-    o->tint_depth = 0;
-    o->thresholds[0] = 0.14; o->thresholds[1] = 0.15; o->thresholds[2] = 0.16; o->thresholds[3] = 0.18;  // Glome.hs:221-224
-    o->tile_first = 0; o->tile_stride = 1; o->want_rgb8 = 0; o->debug_heatmap = 0;
-}
-
-extern "C" int glome_tile_count(int width, int height, int blocksize) {
-    if (width <= 0 || height <= 0 || blocksize <= 0) return 0;
-    TileGeom g = make_geom(width, height, blocksize);
-    return g.ntx * g.nty;
-}
-extern "C" int glome_tile_rect(int width, int height, int blocksize, int i, int32_t rect[4]) {
-    if (width <= 0 || height <= 0 || blocksize <= 0) { g_err = "bad geometry"; return GLOME_EINVAL; }
-    TileGeom g = make_geom(width, height, blocksize);
-    if (i < 0 || i >= g.ntx * g.nty) { g_err = "tile index out of range"; return GLOME_EINVAL; }
-    int tx = i / g.nty, ty = i % g.nty;
-    rect[0] = tx * blocksize; rect[1] = ty * blocksize;
-    rect[2] = (blocksize < width - rect[0]) ? blocksize : width - rect[0];
-    rect[3] = (blocksize < height - rect[1]) ? blocksize : height - rect[1];
-    return GLOME_OK;
-}
-
 static void trav_mark(GlomeScene* s, cudaStream_t st, int family);
 
 template <bool GEN, int MODE>
@@ -1564,11 +1537,6 @@ __global__ void __launch_bounds__(256) k_tiles_copy(TileGeom g, int tile_first, 
         if (PACK) packed[pi] = frame[fi];
         else frame[fi] = packed[pi];
     }
-}
-extern "C" int glome_tile_slots(int width, int height, int blocksize, int tile_stride) {
-    int n = glome_tile_count(width, height, blocksize);
-    if (tile_stride <= 0) return 0;
-    return (n + tile_stride - 1) / tile_stride;
 }
 static int tiles_copy(bool pack, int width, int height, int blocksize, int tile_first, int tile_stride, int elem_bytes,
                       void* frame, void* packed, void* stream) {

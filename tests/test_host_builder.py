@@ -242,3 +242,25 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle" not in src.lower().replace("no oracle", "").replace("touches oracle/", "") or \
                     "import oracle" not in src and "glome_oracle" not in src, f
+
+
+def test_host_library_stands_alone():
+    """libglomehost.so (scene construction) has no CUDA in it, and a process that sets GLOME_HOST_ONLY=1 -- bench.py's CPU
+    reference arm -- builds its scene and runs the oracle without ever mapping libglomecuda.so."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    host = os.path.join(root, "glome_b200", "_build", "libglomehost.so")
+    deps = subprocess.run(["ldd", host], capture_output=True, text=True).stdout
+    assert "cuda" not in deps.lower() and "glomecuda" not in deps
+    code = ("import os,sys; os.environ['GLOME_HOST_ONLY']='1'; sys.path.insert(0,%r); sys.path.insert(0,%r)\n"
+            "import glome_b200 as G, oracle as O\n"
+            "from glome_b200 import _lib as L\n"
+            "b=G.SceneBuilder(); root,cam,rec=b.config_scene(4,3); fs=b.flatten(root)\n"
+            "tc,_=O.OracleScene(fs).render(cam,32,24,G.render_opts(mode=L.MODE_ONE_RAY,recurs=rec))\n"
+            "maps=open('/proc/self/maps').read()\n"
+            "assert 'libglomehost' in maps and 'libglomecuda' not in maps and tc[...,3].max()>0\n"
+            "assert not hasattr(L.load(),'glome_render')\n"
+            "print('ok')\n") % (root, os.path.join(root, "tests"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr
