@@ -150,6 +150,9 @@ SIGNATURES = {
     "glome_sb_group": (C.c_int, [_vp, C.c_int, _vp]),
     "glome_sb_bih": (C.c_int, [_vp, C.c_int64, _vp]),
     "glome_sb_mesh": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int, _vp, C.c_int, _vp]),
+    "glome_sb_bih_prebuilt": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, _vp, _vp, _vp]),
+    "glome_sb_mesh_prebuilt": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int, _vp, C.c_int, _vp,
+                                         C.c_int64, _vp, _vp, C.c_int64, _vp, _vp]),
     "glome_sb_difference": (C.c_int, [_vp, C.c_int, C.c_int]),
     "glome_sb_intersection": (C.c_int, [_vp, C.c_int, _vp]),
     "glome_sb_tex": (C.c_int, [_vp, C.c_int, C.c_int]),

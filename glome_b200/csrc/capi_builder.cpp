@@ -104,6 +104,19 @@ int glome_sb_mesh(GlomeBuilder* b, int64_t nverts, const double* verts, int64_t 
                   const int32_t* tris, int ntexs, const int32_t* texs, int ntags, const int32_t* tags) {
     GUARD(b->b.mesh(nverts, verts, nnorms, norms, ntris, tris, ntexs, texs, ntags, tags));
 }
+int glome_sb_bih_prebuilt(GlomeBuilder* b, int64_t n, const int32_t* items, int64_t n_nodes, const int32_t* kinds,
+                          const double* splits, const double bb[6]) {
+    if (!b || n < 0 || (n > 0 && !items) || !kinds || !splits || !bb) return GLOME_EINVAL;
+    GUARD(b->b.bih_prebuilt(std::vector<int32_t>(items, items + n), n_nodes, kinds, splits, bb));
+}
+int glome_sb_mesh_prebuilt(GlomeBuilder* b, int64_t nverts, const double* verts, int64_t nnorms, const double* norms,
+                           int64_t ntris, const int32_t* tris, int ntexs, const int32_t* texs, int ntags, const int32_t* tags,
+                           int64_t n_nodes, const int32_t* kinds, const double* boxes, int64_t n_leaf_tris,
+                           const int32_t* leaf_tris, const double bb[6]) {
+    if (!b || !verts || !tris || !kinds || !boxes || (n_leaf_tris > 0 && !leaf_tris) || !bb) return GLOME_EINVAL;
+    GUARD(b->b.mesh_prebuilt(nverts, verts, nnorms, norms, ntris, tris, ntexs, texs, ntags, tags, n_nodes, kinds, boxes,
+                             n_leaf_tris, leaf_tris, bb));
+}
 int glome_sb_difference(GlomeBuilder* b, int sa, int sb) { GUARD(b->b.difference(sa, sb)); }
 int glome_sb_intersection(GlomeBuilder* b, int n, const int32_t* items) { GUARD(b->b.intersection(IV(n, items))); }
 int glome_sb_tex(GlomeBuilder* b, int item, int texture) { GUARD(b->b.tex(item, texture)); }

@@ -542,6 +542,134 @@ int Builder::bih(const std::vector<int32_t>& xs) {  // Bih.hs:309-324
     it.kids = xs;
     return add(it);
 }
+// A Bih whose tree the caller already built (the Haskell `bih` constructor: Bih.hs:309-324 returns `Bih bb root`).
+// The tree arrives as a PRE-ORDER stream mirroring the constructors of Bih.hs:51-57:
+//   kinds[i] >= 0 : BihBranch lsplit rsplit axis l r   with axis = kinds[i], lsplit = splits[2i], rsplit = splits[2i+1];
+//                   the records of l follow, then those of r
+//   kinds[i] <  0 : BihLeaf [s]  holding the next  -(kinds[i] + 1)  entries of `xs`
+// so `xs` lists the items in the order the leaves hold them.  The result is the Item glome_sb_bih would have made had
+// its own builder produced this tree (tests/test_host_builder.py imports a tree it built and compares the FlatScenes).
+int Builder::bih_prebuilt(const std::vector<int32_t>& xs, int64_t n_nodes, const int32_t* kinds, const double* splits, const double bb[6]) {
+    if (n_nodes <= 0) throw BuildError("bih_prebuilt: empty tree (an empty bih is Void, Bih.hs:312)");
+    for (size_t i = 0; i < xs.size(); i++) check(xs[i]);
+    bihs.emplace_back();
+    BihTree& T = bihs.back();
+    T.bb = mkbb(vec(bb[0], bb[1], bb[2]), vec(bb[3], bb[4], bb[5]));
+    T.order.resize(xs.size());
+    for (size_t i = 0; i < xs.size(); i++) T.order[i] = (int32_t)i;
+    int64_t cur = 0, item = 0;
+    // explicit stack: (node index whose child slot to fill, which slot); -1 = the root ref
+    struct Pending { int32_t node; int slot; };
+    std::vector<Pending> st;
+    st.push_back({-1, 0});
+    while (!st.empty()) {
+        Pending p = st.back();
+        st.pop_back();
+        if (cur >= n_nodes) throw BuildError("bih_prebuilt: the pre-order stream ends inside a branch");
+        const int32_t k = kinds[cur];
+        int32_t ref;
+        if (k < 0) {
+            const int64_t cnt = -((int64_t)k + 1);
+            if (item + cnt > (int64_t)xs.size()) throw BuildError("bih_prebuilt: leaves hold more items than were passed");
+            ref = ~(int32_t)(T.leaves.size() / 2);
+            T.leaves.push_back((int32_t)item);
+            T.leaves.push_back((int32_t)cnt);
+            item += cnt;
+        } else {
+            if (k > 2) throw BuildError("bih_prebuilt: axis out of range");
+            ref = (int32_t)T.nodes.size();
+            GlomeBihNode nd;
+            memset(&nd, 0, sizeof(nd));
+            nd.lsplit = splits[2 * cur]; nd.rsplit = splits[2 * cur + 1]; nd.axis = k;
+            T.nodes.push_back(nd);
+            st.push_back({ref, 1});  // right is parsed after the whole left subtree
+            st.push_back({ref, 0});
+            if (st.size() > 4096) throw BuildError("bih_prebuilt: tree too deep");
+        }
+        if (p.node < 0) T.root = ref;
+        else if (p.slot == 0) T.nodes[p.node].left = ref;
+        else T.nodes[p.node].right = ref;
+        cur++;
+    }
+    if (cur != n_nodes) throw BuildError("bih_prebuilt: records left over after the tree");
+    if (item != (int64_t)xs.size()) throw BuildError("bih_prebuilt: the leaves do not hold every item");
+    build_ms[0] = build_ms[1] = build_ms[2] = build_ms[3] = 0;
+    Item it = mkitem(GLOME_BIH);
+    it.ia = (int)bihs.size() - 1;
+    it.kids = xs;
+    return add(it);
+}
+
+// A Mesh whose BVH the caller already built (Mesh.hs:36-42: `Branch lbb rbb l r` / `Leaf [Tri]`), same pre-order stream:
+//   kinds[i] >= 0 : Branch with lbb = boxes[12i .. 12i+5], rbb = boxes[12i+6 .. 12i+11]
+//   kinds[i] <  0 : Leaf holding the next -(kinds[i] + 1) entries of leaf_tris (mesh-local triangle indices)
+int Builder::mesh_prebuilt(int64_t nverts, const double* verts, int64_t nnorms, const double* norms, int64_t ntris,
+                           const int32_t* tris, int ntexs, const int32_t* texs, int ntags, const int32_t* tags, int64_t n_nodes,
+                           const int32_t* kinds, const double* boxes, int64_t n_leaf_tris, const int32_t* leaf_tris, const double bb[6]) {
+    if (n_nodes <= 0) throw BuildError("mesh_prebuilt: empty tree");
+    for (int64_t i = 0; i < ntris; i++) {
+        const int32_t* T = tris + 8 * i;
+        for (int j = 0; j < 3; j++)
+            if (T[j] < 0 || T[j] >= nverts) throw BuildError("mesh: vertex index out of range");
+        if (T[3] != -1)
+            for (int j = 3; j < 6; j++)
+                if (T[j] < 0 || T[j] >= nnorms) throw BuildError("mesh: normal index out of range");
+        if (T[6] < -1 || T[6] >= ntexs) throw BuildError("mesh: texture index out of range");
+        if (T[7] < -1 || T[7] >= ntags) throw BuildError("mesh: tag index out of range");
+    }
+    meshes.emplace_back();
+    MeshData& m = meshes.back();
+    m.verts.assign(verts, verts + 3 * nverts);
+    if (nnorms) m.norms.assign(norms, norms + 3 * nnorms);
+    m.tris.assign(tris, tris + 8 * ntris);
+    if (ntexs) m.texs.assign(texs, texs + ntexs);
+    if (ntags) m.tags.assign(tags, tags + ntags);
+    MeshTree& T = m.tree;
+    T.bb = mkbb(vec(bb[0], bb[1], bb[2]), vec(bb[3], bb[4], bb[5]));
+    int64_t cur = 0, tpos = 0;
+    struct Pending { int32_t node; int slot; };
+    std::vector<Pending> st;
+    st.push_back({-1, 0});
+    while (!st.empty()) {
+        Pending p = st.back();
+        st.pop_back();
+        if (cur >= n_nodes) throw BuildError("mesh_prebuilt: the pre-order stream ends inside a branch");
+        const int32_t k = kinds[cur];
+        int32_t ref;
+        if (k < 0) {
+            const int64_t cnt = -((int64_t)k + 1);
+            if (tpos + cnt > n_leaf_tris) throw BuildError("mesh_prebuilt: leaves hold more triangles than were passed");
+            ref = ~(int32_t)T.leafoff.size();
+            T.leafoff.push_back((int32_t)T.leafpool.size());
+            T.leafpool.push_back((int32_t)cnt);
+            for (int64_t q = 0; q < cnt; q++) {
+                if (leaf_tris[tpos + q] < 0 || leaf_tris[tpos + q] >= ntris) throw BuildError("mesh_prebuilt: triangle index out of range");
+                T.leafpool.push_back(leaf_tris[tpos + q]);
+            }
+            tpos += cnt;
+        } else {
+            ref = (int32_t)T.nodes.size();
+            GlomeBvhNode nd;
+            memset(&nd, 0, sizeof(nd));
+            memcpy(nd.lbb, boxes + 12 * cur, 6 * sizeof(double));
+            memcpy(nd.rbb, boxes + 12 * cur + 6, 6 * sizeof(double));
+            T.nodes.push_back(nd);
+            st.push_back({ref, 1});
+            st.push_back({ref, 0});
+            if (st.size() > 4096) throw BuildError("mesh_prebuilt: tree too deep");
+        }
+        if (p.node < 0) T.root = ref;
+        else if (p.slot == 0) T.nodes[p.node].left = ref;
+        else T.nodes[p.node].right = ref;
+        cur++;
+    }
+    if (cur != n_nodes) throw BuildError("mesh_prebuilt: records left over after the tree");
+    if (tpos != n_leaf_tris) throw BuildError("mesh_prebuilt: triangle indices left over after the tree");
+    build_ms[0] = build_ms[1] = build_ms[2] = build_ms[3] = 0;
+    Item it = mkitem(GLOME_MESH);
+    it.ia = (int)meshes.size() - 1;
+    return add(it);
+}
 int Builder::mesh(int64_t nverts, const double* verts, int64_t nnorms, const double* norms, int64_t ntris,
                   const int32_t* tris, int ntexs, const int32_t* texs, int ntags, const int32_t* tags) {
     for (int64_t i = 0; i < ntris; i++) {

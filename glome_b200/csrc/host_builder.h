@@ -103,6 +103,11 @@ class Builder {
     int bih(const std::vector<int32_t>& xs);
     int mesh(int64_t nverts, const double* verts, int64_t nnorms, const double* norms, int64_t ntris,
              const int32_t* tris, int ntexs, const int32_t* texs, int ntags, const int32_t* tags);
+    // trees the caller (the Haskell constructors) already built, as pre-order streams (host_builder.cpp)
+    int bih_prebuilt(const std::vector<int32_t>& xs, int64_t n_nodes, const int32_t* kinds, const double* splits, const double bb[6]);
+    int mesh_prebuilt(int64_t nverts, const double* verts, int64_t nnorms, const double* norms, int64_t ntris,
+                      const int32_t* tris, int ntexs, const int32_t* texs, int ntags, const int32_t* tags, int64_t n_nodes,
+                      const int32_t* kinds, const double* boxes, int64_t n_leaf_tris, const int32_t* leaf_tris, const double bb[6]);
     int difference(int sa, int sb);
     int intersection(const std::vector<int32_t>& xs);
     int tex(int s, int texture);

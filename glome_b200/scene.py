@@ -182,6 +182,51 @@ def mesh_build(verts, tris, device=None):
     return res
 
 
+def bih_preorder_stream(tree):
+    """The pre-order stream glome_sb_bih_prebuilt takes (what a Haskell `Flatten` instance emits while walking
+    `BihBranch lsplit rsplit axis l r | BihLeaf [s]`, Bih.hs:51-57), from the arrays of bih_build: (kinds, splits,
+    leaf-ordered item positions)."""
+    nodes, leaves, order = tree["nodes"], tree["leaves"], tree["order"]
+    kinds, splits, items = [], [], []
+    stack = [tree["root"]]
+    while stack:
+        ref = stack.pop()
+        if ref < 0:
+            first, count = leaves[~ref]
+            kinds.append(-(int(count) + 1))
+            splits.append((0.0, 0.0))
+            items.extend(int(x) for x in order[first:first + count])
+        else:
+            nd = nodes[ref]
+            kinds.append(int(nd["axis"]))
+            splits.append((float(nd["lsplit"]), float(nd["rsplit"])))
+            stack.append(int(nd["right"]))
+            stack.append(int(nd["left"]))
+    return np.array(kinds, np.int32), np.array(splits, np.float64).reshape(-1, 2), np.array(items, np.int32)
+
+
+def mesh_preorder_stream(tree):
+    """Same for `Branch lbb rbb l r | Leaf [Tri]` (Mesh.hs:36-42), from the arrays of mesh_build: (kinds, boxes, leaf_tris)."""
+    nodes, leafpool, leafoff = tree["nodes"], tree["leafpool"], tree["leafoff"]
+    kinds, boxes, tris = [], [], []
+    stack = [tree["root"]]
+    while stack:
+        ref = stack.pop()
+        if ref < 0:
+            off = leafoff[~ref]
+            count = int(leafpool[off])
+            kinds.append(-(count + 1))
+            boxes.append(np.zeros(12))
+            tris.extend(int(x) for x in leafpool[off + 1:off + 1 + count])
+        else:
+            nd = nodes[ref]
+            kinds.append(0)
+            boxes.append(np.concatenate([nd["lbb"], nd["rbb"]]))
+            stack.append(int(nd["right"]))
+            stack.append(int(nd["left"]))
+    return np.array(kinds, np.int32), np.array(boxes, np.float64).reshape(-1, 12), np.array(tris, np.int32)
+
+
 class SceneBuilder:
     """Host mirror of the GlomeTrace construction API.  Items are int ids."""
 
@@ -284,6 +329,22 @@ class SceneBuilder:
         texs, tags = _i32(texs), _i32(tags)
         return L.check(self.lib.glome_sb_mesh(self.h, len(verts), _ptr(verts), len(norms), _ptr(norms), len(tris),
                                               _ptr(tris), len(texs), _ptr(texs), len(tags), _ptr(tags)))
+
+    def bih_prebuilt(self, items, kinds, splits, bb):
+        """A Bih whose tree the caller built (Bih.hs:51-57), as the pre-order stream include/glome_cuda.h describes."""
+        a, kinds, splits, bb = _i32(items), _i32(kinds), _f64(splits, (-1, 2)), _f64(bb, (6,))
+        return L.check(self.lib.glome_sb_bih_prebuilt(self.h, len(a), _ptr(a), len(kinds), _ptr(kinds), _ptr(splits), _ptr(bb)))
+
+    def mesh_prebuilt(self, verts, norms, tris, texs, tags, kinds, boxes, leaf_tris, bb):
+        """A Mesh whose BVH the caller built (Mesh.hs:36-42), same pre-order stream with two boxes per branch."""
+        verts = _f64(verts, (-1, 3))
+        norms = _f64(norms, (-1, 3)) if len(norms) else np.zeros((0, 3))
+        tris = _i32(tris).reshape(-1, 8)
+        texs, tags, kinds, leaf_tris = _i32(texs), _i32(tags), _i32(kinds), _i32(leaf_tris)
+        boxes, bb = _f64(boxes, (-1, 12)), _f64(bb, (6,))
+        return L.check(self.lib.glome_sb_mesh_prebuilt(self.h, len(verts), _ptr(verts), len(norms), _ptr(norms), len(tris),
+                                                       _ptr(tris), len(texs), _ptr(texs), len(tags), _ptr(tags), len(kinds),
+                                                       _ptr(kinds), _ptr(boxes), len(leaf_tris), _ptr(leaf_tris), _ptr(bb)))
 
     def difference(self, sa, sb):
         return L.check(self.lib.glome_sb_difference(self.h, sa, sb))

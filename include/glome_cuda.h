@@ -363,6 +363,21 @@ int glome_sb_bih(GlomeBuilder* b, int64_t n, const int32_t* items);             
 int glome_sb_mesh(GlomeBuilder* b, int64_t nverts, const double* verts, int64_t nnorms,
                   const double* norms, int64_t ntris, const int32_t* tris /*8 per tri*/,
                   int ntexs, const int32_t* texs, int ntags, const int32_t* tags);        /* Mesh.hs:50 */
+/* A `Bih bb root` / `Mesh` whose tree the Haskell constructor ALREADY built (Bih.hs:51-57 `BihBranch lsplit rsplit axis l r`
+ * | `BihLeaf [s]`; Mesh.hs:36-42 `Branch lbb rbb l r` | `Leaf [Tri]`), imported as a PRE-ORDER stream of n_nodes records
+ * (a branch is followed by all records of l, then those of r) instead of being rebuilt:
+ *   kinds[i] >= 0  a branch.  Bih: axis = kinds[i], lsplit = splits[2i], rsplit = splits[2i+1].
+ *                             Mesh: lbb = boxes[12i..12i+5], rbb = boxes[12i+6..12i+11] (p1 then p2); kinds[i] is ignored.
+ *   kinds[i] <  0  a leaf holding the next -(kinds[i]+1) entries of `items` (Bih; items are listed in the order the
+ *                  leaves hold them) or of `leaf_tris` (Mesh; mesh-local triangle indices).
+ * bb = the root box (Bih.hs:323 / Mesh.hs:212).  The item equals the one glome_sb_bih / glome_sb_mesh would return had
+ * their own builders produced that tree (tests/test_host_builder.py).  Malformed streams: GLOME_EBUILD. */
+int glome_sb_bih_prebuilt(GlomeBuilder* b, int64_t n, const int32_t* items, int64_t n_nodes, const int32_t* kinds,
+                          const double* splits, const double bb[6]);                       /* Bih.hs:51-57 */
+int glome_sb_mesh_prebuilt(GlomeBuilder* b, int64_t nverts, const double* verts, int64_t nnorms, const double* norms,
+                           int64_t ntris, const int32_t* tris /*8 per tri*/, int ntexs, const int32_t* texs, int ntags,
+                           const int32_t* tags, int64_t n_nodes, const int32_t* kinds, const double* boxes,
+                           int64_t n_leaf_tris, const int32_t* leaf_tris, const double bb[6]); /* Mesh.hs:36-42 */
 int glome_sb_difference(GlomeBuilder* b, int sa, int sb);                                 /* Csg.hs:26 */
 int glome_sb_intersection(GlomeBuilder* b, int n, const int32_t* items);                  /* Csg.hs:64 */
 int glome_sb_tex(GlomeBuilder* b, int item, int texture);                                 /* Tex.hs:33 */

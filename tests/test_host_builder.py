@@ -244,6 +244,54 @@ def test_product_never_imports_oracle():
                     "import oracle" not in src and "glome_oracle" not in src, f
 
 
+def _flat_bytes(fs):
+    v = G.scene.FlatView(fs)
+    return [v.nodes.tobytes(), v.bihnodes.tobytes(), v.bvhnodes.tobytes(), v.ipool.tobytes(), v.dpool.tobytes(), v.root,
+            v.scene_class, v.max_depth]
+
+
+@pytest.mark.parametrize("n,seed", [(1, 1), (2, 2), (7, 3), (500, 4), (20000, 5)])
+def test_prebuilt_bih_import_equals_own_build(n, seed):
+    """glome_sb_bih_prebuilt: a `Bih bb root` the caller already built (Bih.hs:51-57, 309-324), imported as a pre-order
+    stream, flattens to exactly the FlatScene glome_sb_bih produces by building the tree itself."""
+    rng = np.random.default_rng(seed)
+    c, r = rng.uniform(-10, 10, size=(n, 3)), rng.uniform(0.05, 0.7, size=n)
+    tree = G.scene.bih_build(np.hstack([c - r[:, None], c + r[:, None]]))
+    kinds, splits, pos = G.scene.bih_preorder_stream(tree)
+    a, b = G.SceneBuilder(), G.SceneBuilder()
+    own = a.flatten(a.bih([a.tag(s, i) if i % 3 == 0 else s for i, s in enumerate(a.spheres(c, r))]))
+    ids = [b.tag(s, i) if i % 3 == 0 else s for i, s in enumerate(b.spheres(c, r))]
+    imp = b.flatten(b.bih_prebuilt([ids[p] for p in pos], kinds, splits, tree["bb"]))
+    assert _flat_bytes(own) == _flat_bytes(imp)
+
+
+def test_prebuilt_mesh_import_equals_own_build():
+    """glome_sb_mesh_prebuilt: `Branch lbb rbb l r | Leaf [Tri]` (Mesh.hs:36-42) in pre-order == glome_sb_mesh's own tree."""
+    for g, seed in [(1, 1), (3, 2), (40, 3)]:
+        verts, tris = grid_mesh(g, seed)
+        tris = tris.copy()
+        tris[:, 7] = np.arange(len(tris)) % 5
+        tree = G.scene.mesh_build(verts, tris)
+        kinds, boxes, leaf_tris = G.scene.mesh_preorder_stream(tree)
+        a, b = G.SceneBuilder(), G.SceneBuilder()
+        own = a.flatten(a.mesh(verts, [], tris, [], list(range(5))))
+        imp = b.flatten(b.mesh_prebuilt(verts, [], tris, [], list(range(5)), kinds, boxes, leaf_tris, tree["bb"]))
+        assert _flat_bytes(own) == _flat_bytes(imp)
+
+
+def test_prebuilt_streams_are_validated():
+    b = G.SceneBuilder()
+    s = b.spheres(np.zeros((3, 3)), np.ones(3))
+    bb = [-1, -1, -1, 1, 1, 1]
+    for kinds, splits in [([0, -2], [[0, 0]] * 2),             # branch with one child
+                          ([-3], [[0, 0]]),                    # leaf holds fewer items than passed
+                          ([0, -3, -3], [[0, 0]] * 3),         # leaves hold more than passed
+                          ([5, -2, -3], [[0, 0]] * 3),         # axis out of range
+                          ([-4, -1], [[0, 0]] * 2)]:           # records after the tree
+        with pytest.raises(L.GlomeError):
+            b.bih_prebuilt(s, kinds, splits, bb)
+
+
 def test_host_library_stands_alone():
     """libglomehost.so (scene construction) has no CUDA in it, and a process that sets GLOME_HOST_ONLY=1 -- bench.py's CPU
     reference arm -- builds its scene and runs the oracle without ever mapping libglomecuda.so."""
