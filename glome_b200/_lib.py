@@ -150,6 +150,10 @@ SIGNATURES = {
     "glome_sb_group": (C.c_int, [_vp, C.c_int, _vp]),
     "glome_sb_bih": (C.c_int, [_vp, C.c_int64, _vp]),
     "glome_sb_mesh": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int, _vp, C.c_int, _vp]),
+    "glome_sb_list": (C.c_int, [_vp, C.c_int, _vp]),
+    "glome_sb_instance": (C.c_int, [_vp, C.c_int, _dp]),
+    "glome_sb_disc_raw": (C.c_int, [_vp, _dp, _dp, C.c_double]),
+    "glome_sb_difference_ex": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
     "glome_sb_bih_prebuilt": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, _vp, _vp, _vp]),
     "glome_sb_mesh_prebuilt": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int, _vp, C.c_int, _vp,
                                          C.c_int64, _vp, _vp, C.c_int64, _vp, _vp]),

@@ -99,6 +99,13 @@ int glome_sb_cone(GlomeBuilder* b, const double p1[3], double r1, const double p
 int glome_sb_cylinder_z(GlomeBuilder* b, double r, double h1, double h2) { GUARD(b->b.cylinder_z(r, h1, h2)); }
 int glome_sb_cone_z(GlomeBuilder* b, double r, double h1, double h2, double height) { GUARD(b->b.cone_z(r, h1, h2, height)); }
 int glome_sb_group(GlomeBuilder* b, int n, const int32_t* items) { GUARD(b->b.group(IV(n, items))); }
+// raw forms: the data an already-constructed Haskell value holds, taken as is (no constructor logic re-run)
+int glome_sb_list(GlomeBuilder* b, int n, const int32_t* items) { GUARD(b->b.list_raw(IV(n, items))); }
+int glome_sb_instance(GlomeBuilder* b, int item, const double xfm[24]) { GUARD(b->b.instance_raw(item, X(xfm))); }
+int glome_sb_disc_raw(GlomeBuilder* b, const double pos[3], const double norm[3], double rsqr) {
+    GUARD(b->b.disc_raw(V(pos), V(norm), rsqr));
+}
+int glome_sb_difference_ex(GlomeBuilder* b, int sa, int sb, int useatex) { GUARD(b->b.difference_ex(sa, sb, useatex != 0)); }
 int glome_sb_bih(GlomeBuilder* b, int64_t n, const int32_t* items) { GUARD(b->b.bih(std::vector<int32_t>(items, items + n))); }
 int glome_sb_mesh(GlomeBuilder* b, int64_t nverts, const double* verts, int64_t nnorms, const double* norms, int64_t ntris,
                   const int32_t* tris, int ntexs, const int32_t* texs, int ntags, const int32_t* tags) {

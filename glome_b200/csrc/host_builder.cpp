@@ -473,6 +473,11 @@ int Builder::disc(const Vec& pos, const Vec& norm, Flt r) {  // Cone.hs:29-31
     putv(it, 0, pos); putv(it, 3, norm); it.d[6] = r * r; it.nd = 7;
     return add(it);
 }
+int Builder::disc_raw(const Vec& pos, const Vec& norm, Flt rsqr) {  // Cone.hs:21: the stored fields
+    Item it = mkitem(GLOME_DISC);
+    putv(it, 0, pos); putv(it, 3, norm); it.d[6] = rsqr; it.nd = 7;
+    return add(it);
+}
 int Builder::cylinder_z(Flt r, Flt h1, Flt h2) {  // Cone.hs:33
     Item it = mkitem(GLOME_CYLINDER);
     it.d[0] = r; it.d[1] = h1; it.d[2] = h2; it.nd = 3;
@@ -700,6 +705,11 @@ int Builder::mesh(int64_t nverts, const double* verts, int64_t nnorms, const dou
 int Builder::difference(int sa, int sb) {  // Csg.hs:26-27
     Item it = mkitem(GLOME_DIFFERENCE);
     it.kids.push_back(check(sa)); it.kids.push_back(check(sb)); it.ia = 1;
+    return add(it);
+}
+int Builder::difference_ex(int sa, int sb, bool useatex) {  // Csg.hs:26-30 (difference / difference_retexture)
+    Item it = mkitem(GLOME_DIFFERENCE);
+    it.kids.push_back(check(sa)); it.kids.push_back(check(sb)); it.ia = useatex ? 1 : 0;
     return add(it);
 }
 int Builder::intersection(const std::vector<int32_t>& xs) {  // Csg.hs:64-65

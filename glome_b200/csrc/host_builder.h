@@ -109,6 +109,8 @@ class Builder {
                       const int32_t* tris, int ntexs, const int32_t* texs, int ntags, const int32_t* tags, int64_t n_nodes,
                       const int32_t* kinds, const double* boxes, int64_t n_leaf_tris, const int32_t* leaf_tris, const double bb[6]);
     int difference(int sa, int sb);
+    int difference_ex(int sa, int sb, bool useatex);        // Difference a b Bool as stored (Csg.hs:14, 26-30)
+    int disc_raw(const Vec& pos, const Vec& norm, Flt rsqr); // Disc pos norm (r*r) as stored (Cone.hs:21)
     int intersection(const std::vector<int32_t>& xs);
     int tex(int s, int texture);
     int tag(int s, int tagid);

@@ -330,6 +330,21 @@ class SceneBuilder:
         return L.check(self.lib.glome_sb_mesh(self.h, len(verts), _ptr(verts), len(norms), _ptr(norms), len(tris),
                                               _ptr(tris), len(texs), _ptr(texs), len(tags), _ptr(tags)))
 
+    # raw forms (what the Haskell `flatten` instances call: stored fields, no constructor logic)
+    def list_raw(self, items):
+        a = _i32(items)
+        return L.check(self.lib.glome_sb_list(self.h, len(a), _ptr(a)))
+
+    def instance_raw(self, item, xfm):
+        x = _f64(xfm, (24,))
+        return L.check(self.lib.glome_sb_instance(self.h, item, x.ctypes.data_as(C.POINTER(C.c_double))))
+
+    def disc_raw(self, pos, norm, rsqr):
+        return L.check(self.lib.glome_sb_disc_raw(self.h, _d3(pos), _d3(norm), float(rsqr)))
+
+    def difference_ex(self, sa, sb, useatex):
+        return L.check(self.lib.glome_sb_difference_ex(self.h, sa, sb, 1 if useatex else 0))
+
     def bih_prebuilt(self, items, kinds, splits, bb):
         """A Bih whose tree the caller built (Bih.hs:51-57), as the pre-order stream include/glome_cuda.h describes."""
         a, kinds, splits, bb = _i32(items), _i32(kinds), _f64(splits, (-1, 2)), _f64(bb, (6,))

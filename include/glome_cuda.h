@@ -363,6 +363,12 @@ int glome_sb_bih(GlomeBuilder* b, int64_t n, const int32_t* items);             
 int glome_sb_mesh(GlomeBuilder* b, int64_t nverts, const double* verts, int64_t nnorms,
                   const double* norms, int64_t ntris, const int32_t* tris /*8 per tri*/,
                   int ntexs, const int32_t* texs, int ntags, const int32_t* tags);        /* Mesh.hs:50 */
+/* Raw forms for the Haskell `flatten` instances (haskell/): the fields an already-constructed value holds, taken as they
+ * are -- no constructor logic is re-run, so the device sees the very numbers the CPU path uses. */
+int glome_sb_list(GlomeBuilder* b, int n, const int32_t* items);                          /* [s], Solid.hs:326 (no group flattening) */
+int glome_sb_instance(GlomeBuilder* b, int item, const double xfm[24]);                   /* Instance s xfm, Solid.hs:386 */
+int glome_sb_disc_raw(GlomeBuilder* b, const double pos[3], const double norm[3], double rsqr); /* Disc pos norm (r*r), Cone.hs:21 */
+int glome_sb_difference_ex(GlomeBuilder* b, int sa, int sb, int useatex);                 /* Difference a b Bool, Csg.hs:14,26-30 */
 /* A `Bih bb root` / `Mesh` whose tree the Haskell constructor ALREADY built (Bih.hs:51-57 `BihBranch lsplit rsplit axis l r`
  * | `BihLeaf [s]`; Mesh.hs:36-42 `Branch lbb rbb l r` | `Leaf [Tri]`), imported as a PRE-ORDER stream of n_nodes records
  * (a branch is followed by all records of l, then those of r) instead of being rebuilt:
@@ -470,4 +476,27 @@ void glome_free(void* p);
 #ifdef __cplusplus
 }
 #endif
+
+/* Layout contract of the structs that cross the boundary by address.  The Haskell binding (haskell/Data/Glome/CUDA.hs)
+ * peeks / pokes them at these byte offsets (it has no hsc2hs step); a change here fails the build of the library. */
+#include <stddef.h>
+#ifdef __cplusplus
+#define GLOME_LAYOUT_ASSERT(c) static_assert(c, #c)
+#else
+#define GLOME_LAYOUT_ASSERT(c) _Static_assert(c, #c)
+#endif
+GLOME_LAYOUT_ASSERT(sizeof(GlomeRenderOpts) == 64);
+GLOME_LAYOUT_ASSERT(offsetof(GlomeRenderOpts, mode) == 0 && offsetof(GlomeRenderOpts, blocksize) == 4);
+GLOME_LAYOUT_ASSERT(offsetof(GlomeRenderOpts, recurs) == 8 && offsetof(GlomeRenderOpts, tint_depth) == 12);
+GLOME_LAYOUT_ASSERT(offsetof(GlomeRenderOpts, thresholds) == 16 && offsetof(GlomeRenderOpts, tile_first) == 48);
+GLOME_LAYOUT_ASSERT(offsetof(GlomeRenderOpts, tile_stride) == 52 && offsetof(GlomeRenderOpts, want_rgb8) == 56);
+GLOME_LAYOUT_ASSERT(offsetof(GlomeRenderOpts, debug_heatmap) == 60);
+GLOME_LAYOUT_ASSERT(sizeof(GlomeHit) == 144);
+GLOME_LAYOUT_ASSERT(offsetof(GlomeHit, t) == 0 && offsetof(GlomeHit, pos) == 8 && offsetof(GlomeHit, norm) == 32);
+GLOME_LAYOUT_ASSERT(offsetof(GlomeHit, hit) == 56 && offsetof(GlomeHit, prim) == 60 && offsetof(GlomeHit, sub) == 64);
+GLOME_LAYOUT_ASSERT(offsetof(GlomeHit, ntex) == 68 && offsetof(GlomeHit, ntag) == 72 && offsetof(GlomeHit, flags) == 76);
+GLOME_LAYOUT_ASSERT(offsetof(GlomeHit, tex) == 80 && offsetof(GlomeHit, tag) == 112);
+GLOME_LAYOUT_ASSERT(sizeof(GlomeCamera) == 96);   /* pos, fwd, up, right: 12 doubles */
+GLOME_LAYOUT_ASSERT(sizeof(GlomeFlatScene) <= 256); /* the binding allocates 256 bytes for glome_sb_flatten's output */
+GLOME_LAYOUT_ASSERT(sizeof(GlomeBihNode) == 32 && sizeof(GlomeBvhNode) == 128 && sizeof(GlomeNode) == 16);
 #endif /* GLOME_CUDA_H */

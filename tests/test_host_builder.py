@@ -279,6 +279,30 @@ def test_prebuilt_mesh_import_equals_own_build():
         assert _flat_bytes(own) == _flat_bytes(imp)
 
 
+def test_raw_forms_equal_the_constructors():
+    """glome_sb_list / _instance / _disc_raw / _difference_ex take the fields a constructed Haskell value stores
+    ([s]; Instance s xfm, Solid.hs:386; Disc pos norm (r*r), Cone.hs:21; Difference a b Bool, Csg.hs:14)."""
+    a, b = G.SceneBuilder(), G.SceneBuilder()
+    x = G.compose([G.scale((1, 2, 3)), G.translate((1, 0, -2))])
+
+    def scene(bl, raw):
+        s1, s2 = bl.sphere((0, 0, 0), 1.0), bl.box((-1, -1, -1), (0.5, 2, 1))
+        d = bl.disc_raw((0, 1, 0), (0, 1, 0), 0.7 * 0.7) if raw else bl.disc((0, 1, 0), (0, 1, 0), 0.7)
+        df = bl.difference_ex(s1, s2, True) if raw else bl.difference(s1, s2)
+        ins = bl.instance_raw(df, x) if raw else bl.transform(df, [x])
+        return bl.flatten((bl.list_raw if raw else bl.group)([ins, d, bl.sphere((3, 0, 0), 0.5)]))
+
+    assert _flat_bytes(scene(a, False)) == _flat_bytes(scene(b, True))
+    c = G.SceneBuilder()
+    keep = c.flatten(c.list_raw([c.list_raw([c.sphere((0, 0, 0), 1)]), c.void()]))  # no flattening, Void kept
+    assert G.scene.FlatView(keep).nodes["type"].tolist().count(9) == 2  # GLOME_GROUP
+    d0, d1 = G.SceneBuilder(), G.SceneBuilder()
+    f0 = d0.flatten(d0.difference_ex(d0.sphere((0, 0, 0), 1), d0.sphere((1, 0, 0), 1), False))
+    f1 = d1.flatten(d1.difference(d1.sphere((0, 0, 0), 1), d1.sphere((1, 0, 0), 1)))
+    n0, n1 = G.scene.FlatView(f0).nodes, G.scene.FlatView(f1).nodes
+    assert n0[f0.root]["c"] == 0 and n1[f1.root]["c"] == 1  # difference_retexture vs difference (Csg.hs:26-30)
+
+
 def test_prebuilt_streams_are_validated():
     b = G.SceneBuilder()
     s = b.spheres(np.zeros((3, 3)), np.ones(3))
