@@ -320,6 +320,45 @@ def measure(X, cfg, steps, warmup, with_cpu, cpu_seconds, setup_report=False):
     e2e_ms_per_step = e2e_t.item() / n_e2e
     e2e_value = rays_frame / (e2e_ms_per_step * 1e-3) / 1e6
 
+    # ---- the optional FP32 mode, reported separately (north_star; never the headline): the same frame with
+    # Flt = Float on this GPU, device-resident like `value`, and how far its frame is from the FP64 one ----
+    fp32 = None
+    if world == 1:
+        try:
+            s32 = G.Scene(fs, local_rank, precision=32)
+            tc64 = torch.zeros((h, w, 5), dtype=torch.float64, device="cuda")
+            tc32 = torch.zeros((h, w, 5), dtype=torch.float64, device="cuda")
+            o1 = G.render_opts(mode=mode, recurs=recurs)
+            cs = torch.cuda.current_stream().cuda_stream
+            scene.render_ptr(cam, w, h, o1, tc64.data_ptr(), 0, dev=True, stream=cs)
+            for _ in range(3):
+                st32 = s32.render_ptr(cam, w, h, o1, tc32.data_ptr(), 0, dev=True, stream=cs)
+            torch.cuda.synchronize()
+            ev32 = []
+            n32 = max(3, min(steps, 10))
+            for _ in range(n32):
+                X.flush.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                s32.render_ptr(cam, w, h, o1, tc32.data_ptr(), 0, dev=True, stream=cs, want_stats=False)
+                e1.record()
+                ev32.append((e0, e1))
+            torch.cuda.synchronize()
+            ms32 = sum(a.elapsed_time(bb) for a, bb in ev32) / n32
+            rays32 = st32.rays_primary + st32.rays_shadow + st32.rays_secondary
+            d = (tc32[..., :4] - tc64[..., :4]).abs().amax(dim=-1)
+            fp32 = {"dtype": "f32", "ms_per_step": ms32, "fps": 1000.0 / ms32, "value": rays32 / (ms32 * 1e-3) / 1e6,
+                    "unit": "Mrays/s", "speedup_over_f64": ms_per_step / ms32,
+                    "rgba_within_1e-3_of_f64": float((d <= 1e-3).double().mean().item()),
+                    "rgba_median_abs_diff": float(d.median().item()),
+                    "note": "Flt = Float (Vec.hs:7-9): payloads rounded once at upload, 16-byte BIH nodes / 64-byte BVH nodes; "
+                            "pixels beyond 1e-3 are silhouette and shadow-edge pixels where the FP32 walk picks another "
+                            "primitive (tests/test_gpu_f32.py)"}
+            s32.close()
+            del tc64, tc32
+        except Exception as e:
+            fp32 = {"dtype": "f32", "error": repr(e)}
+
     res = None
     if rank == 0:
         peaks, which = measured_peaks()
@@ -382,6 +421,8 @@ def measure(X, cfg, steps, warmup, with_cpu, cpu_seconds, setup_report=False):
         }
         if setup:
             res["scene_setup"] = setup
+        if fp32:
+            res["fp32"] = fp32
         if with_cpu and world == 1:
             threads = os.cpu_count() or 1
             r = cpu_sample(G, cfg, fs, cam, recurs, cpu_seconds, threads)
@@ -453,7 +494,7 @@ def main():
             "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": clocks, "roofline": head["roofline"],
             "wall_s_timed_region": head["wall_s_timed_region"],
         }
-        for k in ("scene_setup", "cpu_baseline"):
+        for k in ("scene_setup", "cpu_baseline", "fp32"):
             if k in head:
                 line[k] = head[k]
         if X.world == 1 and not args.no_all_configs:

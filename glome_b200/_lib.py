@@ -105,6 +105,7 @@ SIGNATURES = {
     "glome_last_error": (C.c_char_p, []),
     "glome_device_count": (C.c_int, []),
     "glome_scene_create": (C.c_int, [_P(GlomeFlatScene), C.c_int, _P(_vp)]),
+    "glome_scene_create_f32": (C.c_int, [_P(GlomeFlatScene), C.c_int, _P(_vp)]),
     "glome_scene_destroy": (C.c_int, [_vp]),
     "glome_rayint_batch": (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_int, _vp]),
     "glome_shadow_batch": (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_int, _vp]),

@@ -8,6 +8,26 @@
 //   K4 pack       rgbf / blitTile
 // The trace kernel is persistent: one grid sized to the SM count, warps pull 32-sample chunks
 // from an atomic counter, so queue lengths never travel to the host.
+// Precision twins.  This file is compiled twice: as it is (FP64, GlomeVec's `type Flt = Double`, Vec.hs:9) and through
+// glome_cuda_f32.cu with GLOME_F32 defined (the Float instance Vec.hs:7-8 leaves as a to-do: the optional FP32 mode).
+// The FP32 copy lives in its own namespaces and exports every scene-bound entry with an `_f32` suffix; the FP64 entries
+// forward to them when the handle says so (GlomeScene.precision), so a caller only chooses at glome_scene_create[_f32].
+#ifdef GLOME_F32
+#define glm glm_f32
+#define gdev gdev_f32
+#define gwave gwave_f32
+#define ggen ggen_f32
+#define glome_tagmap glome_tagmap_f32
+#define GlomeScene GlomeScene_f32
+#define GlomeMulti GlomeMulti_f32
+#define GLOME_API(n) n##_f32
+#define GLOME_PREC_NS glome_prec_f32
+#define GLOME_PRECISION 32
+#else
+#define GLOME_API(n) n
+#define GLOME_PREC_NS glome_prec_f64
+#define GLOME_PRECISION 64
+#endif
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -51,6 +71,8 @@ std::string& glome_err_ref();  // host_base.cpp (libglomehost.so): the C-ABI's t
         }                                                                                          \
     } while (0)
 
+namespace GLOME_PREC_NS {  // this file's own kernels and types, once per precision
+
 // ---------------------------------------------------------------------------------------------
 // device-side helpers shared by kernels
 // ---------------------------------------------------------------------------------------------
@@ -93,13 +115,13 @@ __device__ __forceinline__ Flt cCmp(const TC& p, const TC& q) {  // Glome.hs:179
 }
 __device__ __forceinline__ TC cAvg(const TC& a, const TC& b, const TC& c, const TC& d) {  // Glome.hs:191-197
     TC r;
-    r.r = (a.r + b.r + c.r + d.r) * 0.25; r.g = (a.g + b.g + c.g + d.g) * 0.25; r.b = (a.b + b.b + c.b + d.b) * 0.25;
-    r.a = (a.a + b.a + c.a + d.a) * 0.25; r.d = (a.d + b.d + c.d + d.d) * 0.25;
+    r.r = (a.r + b.r + c.r + d.r) * FL(0.25); r.g = (a.g + b.g + c.g + d.g) * FL(0.25); r.b = (a.b + b.b + c.b + d.b) * FL(0.25);
+    r.a = (a.a + b.a + c.a + d.a) * FL(0.25); r.d = (a.d + b.d + c.d + d.d) * FL(0.25);
     return r;
 }
 __device__ __forceinline__ TC cAvg2(const TC& a, const TC& b) {  // Glome.hs:199-205
     TC r;
-    r.r = (a.r + b.r) * 0.5; r.g = (a.g + b.g) * 0.5; r.b = (a.b + b.b) * 0.5; r.a = (a.a + b.a) * 0.5; r.d = (a.d + b.d) * 0.5;
+    r.r = (a.r + b.r) * FL(0.5); r.g = (a.g + b.g) * FL(0.5); r.b = (a.b + b.b) * FL(0.5); r.a = (a.a + b.a) * FL(0.5); r.d = (a.d + b.d) * FL(0.5);
     return r;
 }
 __device__ __forceinline__ TC tc_init() { TC c; c.r = 0; c.g = 0; c.b = 0; c.a = 0; c.d = GLM_INFINITY; return c; }
@@ -349,7 +371,7 @@ __global__ void __launch_bounds__(128, 1) k_trace_samples(DScene S, TraceParams 
         }
         if (valid) {
             Flt xc, yc;
-            if (MODE == 5) getCoordsf(P.g.width, P.g.height, (Flt)x + 0.5, (Flt)y + 0.5, xc, yc);
+            if (MODE == 5) getCoordsf(P.g.width, P.g.height, (Flt)x + FL(0.5), (Flt)y + FL(0.5), xc, yc);
             else getCoordsf(P.g.width, P.g.height, (Flt)x, (Flt)y, xc, yc);
             ColorA c;
             Flt hd;
@@ -448,7 +470,7 @@ __global__ void __launch_bounds__(GEN_THREADS, GEN_MINBLOCKS) k_gen_trace(DScene
         sr.st = ggen::SS_FINISHED;
         if (valid) {
             Flt xc, yc;
-            if (MODE == 5) getCoordsf(P.g.width, P.g.height, (Flt)px + 0.5, (Flt)py + 0.5, xc, yc);
+            if (MODE == 5) getCoordsf(P.g.width, P.g.height, (Flt)px + FL(0.5), (Flt)py + FL(0.5), xc, yc);
             else getCoordsf(P.g.width, P.g.height, (Flt)px, (Flt)py, xc, yc);
             ggen::shm_start(sr, sh, 0, S.root, camera_ray(P.cam, xc, yc), GLM_INFINITY, P.recurs, nullptr);
         }
@@ -608,10 +630,14 @@ __global__ void __launch_bounds__(256) k_pack_rgb8(TileGeom g, int tile_first, i
     }
 }
 
+}  // namespace GLOME_PREC_NS
+using namespace GLOME_PREC_NS;
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-struct GlomeScene {
+struct GlomeScene {  // (global scope: the C-ABI's opaque handle)
+    int precision;   // 64 or 32: FIRST member of both precision twins' handles
     int device;
     int scene_class;
     int sm_count;
@@ -638,8 +664,8 @@ struct GlomeScene {
     std::vector<int> segs_linear;
     gwave::Seg* segs_dev;
     size_t wave_cap;           // samples
-    double* w_hit_t; int* w_hit_seg; int* w_hit_item; int* w_hit_sub; int* w_hit_flags;
-    double* w_surf; unsigned int* w_occl; int2* w_squeue; int* w_squeue_count;
+    Flt* w_hit_t; int* w_hit_seg; int* w_hit_item; int* w_hit_sub; int* w_hit_flags;
+    Flt* w_surf; unsigned int* w_occl; int2* w_squeue; int* w_squeue_count;
     unsigned int* w_counters;  // one work counter per persistent launch of a frame
     int w_counter_next;
     std::vector<cudaEvent_t> tev;  // start/stop pairs around the traversal kernels of the last timed frame
@@ -655,11 +681,38 @@ struct GlomeScene {
     int aa_w, aa_h, aa_first, aa_stride, aa_bs;
 };
 
+#ifndef GLOME_F32
+// the FP32 twin's entries (glome_cuda_f32.cu); a handle created by glome_scene_create_f32 is forwarded to them
+extern "C" {
+int glome_scene_destroy_f32(GlomeScene* s);
+int glome_rayint_batch_f32(GlomeScene* s, int64_t n, const double* rays, const double* tmax, int tmax_stride, GlomeHit* out);
+int glome_shadow_batch_f32(GlomeScene* s, int64_t n, const double* rays, const double* tmax, int tmax_stride, uint8_t* out);
+int glome_inside_batch_f32(GlomeScene* s, int64_t n, const double* pts, uint8_t* inside);
+int glome_trace_batch_f32(GlomeScene* s, int64_t n, const double* rays, const double* tmax, int tmax_stride, int recurs,
+                          double* rgba, double* depth, GlomeHit* hits);
+int glome_get_tags_f32(GlomeScene* s, const GlomeCamera* cam, int width, int height, int px, int py, int recurs, int32_t* tags,
+                       int max_tags, int* ntags, int* truncated, GlomeHit* hit_out);
+int glome_debug_count_batch_f32(GlomeScene* s, int64_t n, const double* rays, const double* tmax, int tmax_stride, int32_t* counts);
+int glome_render_dev_f32(GlomeScene* s, const GlomeCamera* cam, int width, int height, const GlomeRenderOpts* o, double* tcolor_dev,
+                         uint32_t* rgb8_dev, GlomeRenderStats* stats, void* stream);
+int glome_render_f32(GlomeScene* s, const GlomeCamera* cam, int width, int height, const GlomeRenderOpts* o, double* tcolor,
+                     uint32_t* rgb8, GlomeRenderStats* stats);
+int64_t glome_scene_launches_f32(GlomeScene* s);
+}
+#define TWIN(call) do { if (s && s->precision == 32) return call; } while (0)
+#else
+#define TWIN(call) do { } while (0)
+#endif
+
+namespace GLOME_PREC_NS {
+
+#ifndef GLOME_F32
 extern "C" int glome_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
     return n;
 }
+#endif
 
 template <typename T, typename D>
 static int upload(GlomeScene* s, const T* src, size_t n, D* dst) {
@@ -832,8 +885,9 @@ static int env_int(const char* name, int dflt) {
 }
 
 static int scene_create_impl(GlomeScene* s, const GlomeFlatScene* desc, int device);
+extern "C" int GLOME_API(glome_scene_destroy)(GlomeScene* s);
 
-extern "C" int glome_scene_create(const GlomeFlatScene* desc, int device, GlomeScene** out) {
+extern "C" int GLOME_API(glome_scene_create)(const GlomeFlatScene* desc, int device, GlomeScene** out) {
     if (!out) { g_err = "null out"; return GLOME_EINVAL; }
     *out = nullptr;
     int rc = validate(desc);
@@ -858,7 +912,7 @@ extern "C" int glome_scene_create(const GlomeFlatScene* desc, int device, GlomeS
     }
     if (rc) {
         std::string keep = g_err;
-        if (s) glome_scene_destroy(s);
+        if (s) GLOME_API(glome_scene_destroy)(s);
         g_err = keep;
         return rc;
     }
@@ -868,6 +922,7 @@ extern "C" int glome_scene_create(const GlomeFlatScene* desc, int device, GlomeS
 
 static int scene_create_impl(GlomeScene* s, const GlomeFlatScene* desc, int device) {
     int rc;
+    s->precision = GLOME_PRECISION;
     s->device = device;
     s->scene_class = desc->scene_class;
     cudaDeviceProp prop;
@@ -897,9 +952,32 @@ static int scene_create_impl(GlomeScene* s, const GlomeFlatScene* desc, int devi
         if ((rc = upload(s, desc->nodes, (size_t)desc->n_nodes, &s->d.nodes))) return rc;
         if ((rc = upload(s, desc->ipool, (size_t)desc->n_ipool, &s->d.ipool))) return rc;
     }
+#ifdef GLOME_F32
+    {   // FP32 payloads: round every double once, here; refs and indices are unchanged
+        std::vector<DBihNode> bih((size_t)desc->n_bihnodes);
+        for (int i = 0; i < desc->n_bihnodes; i++) {
+            const GlomeBihNode& b = desc->bihnodes[i];
+            if (b.right > 0x1fffffff || b.right < -0x20000000) { g_err = "FP32 mode: a BIH child ref needs more than 30 bits"; return GLOME_ELIMIT; }
+            bih[i].lsplit = (float)b.lsplit; bih[i].rsplit = (float)b.rsplit; bih[i].left = b.left;
+            bih[i].right_axis = (int32_t)(((uint32_t)b.right << 2) | (uint32_t)b.axis);
+        }
+        std::vector<DBvhNode> bvh((size_t)desc->n_bvhnodes);
+        for (int i = 0; i < desc->n_bvhnodes; i++) {
+            const GlomeBvhNode& b = desc->bvhnodes[i];
+            for (int k = 0; k < 6; k++) { bvh[i].lbb[k] = (float)b.lbb[k]; bvh[i].rbb[k] = (float)b.rbb[k]; }
+            bvh[i].left = b.left; bvh[i].right = b.right; bvh[i].pad[0] = bvh[i].pad[1] = 0;
+        }
+        std::vector<float> dp((size_t)desc->n_dpool);
+        for (int64_t i = 0; i < desc->n_dpool; i++) dp[(size_t)i] = (float)desc->dpool[i];
+        if ((rc = upload(s, bih.data(), bih.size(), &s->d.bih))) return rc;
+        if ((rc = upload(s, bvh.data(), bvh.size(), &s->d.bvh))) return rc;
+        if ((rc = upload(s, dp.data(), dp.size(), &s->d.dpool))) return rc;
+    }
+#else
     if ((rc = upload(s, desc->bihnodes, (size_t)desc->n_bihnodes, &s->d.bih))) return rc;
     if ((rc = upload(s, desc->bvhnodes, (size_t)desc->n_bvhnodes, &s->d.bvh))) return rc;
     if ((rc = upload(s, desc->dpool, (size_t)desc->n_dpool, &s->d.dpool))) return rc;
+#endif
     if ((rc = upload(s, desc->textures, (size_t)desc->n_textures, &s->d.textures))) return rc;
     if ((rc = upload(s, desc->materials, (size_t)desc->n_materials, &s->d.materials))) return rc;
     if ((rc = upload(s, desc->lights, (size_t)desc->n_lights, &s->d.lights))) return rc;
@@ -942,8 +1020,9 @@ static int scene_create_impl(GlomeScene* s, const GlomeFlatScene* desc, int devi
     return GLOME_OK;
 }
 
-extern "C" int glome_scene_destroy(GlomeScene* s) {
+extern "C" int GLOME_API(glome_scene_destroy)(GlomeScene* s) {
     if (!s) return GLOME_OK;
+    TWIN(glome_scene_destroy_f32(s));
     cudaSetDevice(s->device);
     for (void* p : s->bufs) cudaFree(p);
     cudaFree(s->v); cudaFree(s->v2); cudaFree(s->rgb8); cudaFree(s->queue); cudaFree(s->spec);
@@ -977,8 +1056,9 @@ static int batch_grid(GlomeScene* s, long long n) {
     return (int)blocks;
 }
 
-extern "C" int glome_rayint_batch(GlomeScene* s, int64_t n, const double* rays, const double* tmax, int tmax_stride,
+extern "C" int GLOME_API(glome_rayint_batch)(GlomeScene* s, int64_t n, const double* rays, const double* tmax, int tmax_stride,
                                   GlomeHit* out) {
+    TWIN(glome_rayint_batch_f32(s, n, rays, tmax, tmax_stride, out));
     if (!s || n < 0 || !rays || !tmax || !out) { g_err = "bad argument"; return GLOME_EINVAL; }
     if (n == 0) return GLOME_OK;
     CK(cudaSetDevice(s->device));
@@ -1000,8 +1080,9 @@ extern "C" int glome_rayint_batch(GlomeScene* s, int64_t n, const double* rays, 
     return GLOME_OK;
 }
 
-extern "C" int glome_shadow_batch(GlomeScene* s, int64_t n, const double* rays, const double* tmax, int tmax_stride,
+extern "C" int GLOME_API(glome_shadow_batch)(GlomeScene* s, int64_t n, const double* rays, const double* tmax, int tmax_stride,
                                   uint8_t* occluded) {
+    TWIN(glome_shadow_batch_f32(s, n, rays, tmax, tmax_stride, occluded));
     if (!s || n < 0 || !rays || !tmax || !occluded) { g_err = "bad argument"; return GLOME_EINVAL; }
     if (n == 0) return GLOME_OK;
     CK(cudaSetDevice(s->device));
@@ -1023,7 +1104,8 @@ extern "C" int glome_shadow_batch(GlomeScene* s, int64_t n, const double* rays, 
     return GLOME_OK;
 }
 
-extern "C" int glome_inside_batch(GlomeScene* s, int64_t n, const double* pts, uint8_t* inside) {
+extern "C" int GLOME_API(glome_inside_batch)(GlomeScene* s, int64_t n, const double* pts, uint8_t* inside) {
+    TWIN(glome_inside_batch_f32(s, n, pts, inside));
     if (!s || n < 0 || !pts || !inside) { g_err = "bad argument"; return GLOME_EINVAL; }
     if (n == 0) return GLOME_OK;
     CK(cudaSetDevice(s->device));
@@ -1062,8 +1144,9 @@ static void read_stats(GlomeScene* s, GlomeRenderStats* out, float ms, int launc
     out->csg_steps = (int64_t)h.csg;
 }
 
-extern "C" int glome_trace_batch(GlomeScene* s, int64_t n, const double* rays, const double* tmax, int tmax_stride, int recurs,
+extern "C" int GLOME_API(glome_trace_batch)(GlomeScene* s, int64_t n, const double* rays, const double* tmax, int tmax_stride, int recurs,
                                  double* rgba, double* depth, GlomeHit* hits) {
+    TWIN(glome_trace_batch_f32(s, n, rays, tmax, tmax_stride, recurs, rgba, depth, hits));
     if (!s || n < 0 || !rays || !tmax || !rgba || !depth) { g_err = "bad argument"; return GLOME_EINVAL; }
     if (n == 0) return GLOME_OK;
     CK(cudaSetDevice(s->device));
@@ -1097,8 +1180,9 @@ extern "C" int glome_trace_batch(GlomeScene* s, int64_t n, const double* rays, c
 // GlomeView prints on a mouse click.  One camera ray (getCoords, Glome.hs:119-128; get_rayint, :27-33) through
 // trace instantiated with a tag list: `ts ++ tags`, the tags gathered by Reflect / Refract / Warp recursion
 // followed by the hit's own tag stack (Trace.hs:82).
-extern "C" int glome_get_tags(GlomeScene* s, const GlomeCamera* cam, int width, int height, int px, int py, int recurs,
+extern "C" int GLOME_API(glome_get_tags)(GlomeScene* s, const GlomeCamera* cam, int width, int height, int px, int py, int recurs,
                               int32_t* tags, int max_tags, int* ntags, int* truncated, GlomeHit* hit_out) {
+    TWIN(glome_get_tags_f32(s, cam, width, height, px, py, recurs, tags, max_tags, ntags, truncated, hit_out));
     if (!s || !cam || !tags || !ntags || width <= 0 || height <= 0 || max_tags < 0) { g_err = "bad argument"; return GLOME_EINVAL; }
     const Flt xf = (Flt)px, yf = (Flt)py, widthf = (Flt)width, heightf = (Flt)height;
     const Flt xc = (((xf / widthf) * 2) - 1) * (widthf / heightf);
@@ -1161,8 +1245,9 @@ __global__ void k_debug_tint(DScene S, TileGeom g, DCamera cam, int tile_first, 
     out[5 * pix] = ((Flt)(dbg % 30) / 60) + out[5 * pix];
     out[5 * pix + 1] = out[5 * pix + 1] + ((Flt)dbg / 1000);
 }
-extern "C" int glome_debug_count_batch(GlomeScene* s, int64_t n, const double* rays, const double* tmax, int tmax_stride,
+extern "C" int GLOME_API(glome_debug_count_batch)(GlomeScene* s, int64_t n, const double* rays, const double* tmax, int tmax_stride,
                                        int32_t* counts) {
+    TWIN(glome_debug_count_batch_f32(s, n, rays, tmax, tmax_stride, counts));
     if (!s || n < 0 || !rays || !tmax || !counts) { g_err = "bad argument"; return GLOME_EINVAL; }
     if (n == 0) return GLOME_OK;
     CK(cudaSetDevice(s->device));
@@ -1212,12 +1297,12 @@ static int wave_reserve(GlomeScene* s, size_t samples) {
     cudaFree(s->w_surf); cudaFree(s->w_occl); cudaFree(s->w_squeue);
     s->wave_cap = 0;
     int nl = s->n_scene_lights > 0 ? s->n_scene_lights : 1;
-    CK(cudaMalloc((void**)&s->w_hit_t, samples * sizeof(double)));
+    CK(cudaMalloc((void**)&s->w_hit_t, samples * sizeof(Flt)));
     CK(cudaMalloc((void**)&s->w_hit_seg, samples * sizeof(int)));
     CK(cudaMalloc((void**)&s->w_hit_item, samples * sizeof(int)));
     CK(cudaMalloc((void**)&s->w_hit_sub, samples * sizeof(int)));
     CK(cudaMalloc((void**)&s->w_hit_flags, samples * sizeof(int)));
-    CK(cudaMalloc((void**)&s->w_surf, samples * 6 * sizeof(double)));
+    CK(cudaMalloc((void**)&s->w_surf, samples * 6 * sizeof(Flt)));
     CK(cudaMalloc((void**)&s->w_occl, samples * sizeof(unsigned int)));
     CK(cudaMalloc((void**)&s->w_squeue, samples * nl * sizeof(int2)));
     s->wave_cap = samples;
@@ -1299,8 +1384,9 @@ static int launch_wave(GlomeScene* s, gwave::WaveParams W, long long max_samples
     return GLOME_OK;
 }
 
-extern "C" int glome_render_dev(GlomeScene* s, const GlomeCamera* cam, int width, int height, const GlomeRenderOpts* o,
+extern "C" int GLOME_API(glome_render_dev)(GlomeScene* s, const GlomeCamera* cam, int width, int height, const GlomeRenderOpts* o,
                                 double* tcolor_dev, uint32_t* rgb8_dev, GlomeRenderStats* stats, void* stream) {
+    TWIN(glome_render_dev_f32(s, cam, width, height, o, tcolor_dev, rgb8_dev, stats, stream));
     if (!s || !cam || !o || !tcolor_dev || width <= 0 || height <= 0 || o->blocksize <= 0 || o->tile_stride <= 0 ||
         o->tile_first < 0 || o->tile_first >= o->tile_stride) { g_err = "bad argument"; return GLOME_EINVAL; }
     if (o->debug_heatmap && (o->mode != GLOME_MODE_ONE_RAY || o->tint_depth)) {
@@ -1470,8 +1556,9 @@ extern "C" int glome_render_dev(GlomeScene* s, const GlomeCamera* cam, int width
     return GLOME_OK;
 }
 
-extern "C" int glome_render(GlomeScene* s, const GlomeCamera* cam, int width, int height, const GlomeRenderOpts* o,
+extern "C" int GLOME_API(glome_render)(GlomeScene* s, const GlomeCamera* cam, int width, int height, const GlomeRenderOpts* o,
                             double* tcolor, uint32_t* rgb8, GlomeRenderStats* stats) {
+    TWIN(glome_render_f32(s, cam, width, height, o, tcolor, rgb8, stats));
     if (!s || (!tcolor && !rgb8) || width <= 0 || height <= 0) { g_err = "bad argument"; return GLOME_EINVAL; }
     CK(cudaSetDevice(s->device));
     size_t npix = (size_t)width * height;
@@ -1491,7 +1578,7 @@ extern "C" int glome_render(GlomeScene* s, const GlomeCamera* cam, int width, in
         if (rgb8) CK(cudaMemcpy(s->rgb8, rgb8, npix * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
     GlomeRenderStats local;
-    int rc = glome_render_dev(s, cam, width, height, o, s->v2, rgb8 ? s->rgb8 : nullptr, &local, nullptr);
+    int rc = GLOME_API(glome_render_dev)(s, cam, width, height, o, s->v2, rgb8 ? s->rgb8 : nullptr, &local, nullptr);
     if (rc) return rc;
     if (tcolor) CK(cudaMemcpy(tcolor, s->v2, npix * 5 * sizeof(double), cudaMemcpyDeviceToHost));
     if (rgb8) CK(cudaMemcpy(rgb8, s->rgb8, npix * sizeof(uint32_t), cudaMemcpyDeviceToHost));
@@ -1499,8 +1586,12 @@ extern "C" int glome_render(GlomeScene* s, const GlomeCamera* cam, int width, in
     return GLOME_OK;
 }
 
-extern "C" int64_t glome_scene_launches(GlomeScene* s) { return s ? (int64_t)s->launches : 0; }
+extern "C" int64_t GLOME_API(glome_scene_launches)(GlomeScene* s) {
+    TWIN(glome_scene_launches_f32(s));
+    return s ? (int64_t)s->launches : 0;
+}
 
+#ifndef GLOME_F32  // device memory helpers, tile plumbing and the several-GPUs-in-one-process driver exist once (they hold FP64 scenes)
 extern "C" int glome_dev_alloc(int device, int64_t bytes, void** out) {
     if (!out || bytes < 0) { g_err = "bad argument"; return GLOME_EINVAL; }
     CK(cudaSetDevice(device));
@@ -1754,4 +1845,6 @@ extern "C" int glome_multi_render(GlomeMulti* m, const GlomeCamera* cam, int wid
     }
     return GLOME_OK;
 }
+#endif  // !GLOME_F32
 
+}  // namespace GLOME_PREC_NS

@@ -44,12 +44,27 @@ GD_FN T gd_ldg(const T* p) {
 #endif
 }
 
+// Device records of the working precision.  FP64: the FlatScene's own records.  FP32 (GLOME_F32): payloads converted at
+// upload -- a 16-byte BIH node (one load; axis rides in the low two bits of the right ref) and a 64-byte BVH node.
+#ifdef GLOME_F32
+typedef float2 Flt2;
+struct DBihNode { float lsplit, rsplit; int32_t left, right_axis; };
+struct DBvhNode { float lbb[6], rbb[6]; int32_t left, right; int32_t pad[2]; };
+#define GLM_BIG FL(3.0e38)
+#else
+typedef double2 Flt2;
+typedef GlomeBihNode DBihNode;
+typedef GlomeBvhNode DBvhNode;
+#define GLM_BIG FL(1.0e300)
+#endif
+static_assert(sizeof(DBihNode) % 16 == 0 && sizeof(DBvhNode) % 16 == 0, "node records are read with 16-byte loads");
+
 struct DScene {
     const GlomeNode* __restrict__ nodes;
-    const GlomeBihNode* __restrict__ bih;
-    const GlomeBvhNode* __restrict__ bvh;
+    const DBihNode* __restrict__ bih;
+    const DBvhNode* __restrict__ bvh;
     const int32_t* __restrict__ ipool;
-    const double* __restrict__ dpool;
+    const Flt* __restrict__ dpool;
     const GlomeTexture* __restrict__ textures;
     const GlomeMaterial* __restrict__ materials;
     const GlomeLight* __restrict__ lights;
@@ -114,23 +129,67 @@ GD_FN void fold_nearest(Hit& acc, const Hit& c) {
     acc.flags = fl;
 }
 
-GD_FN Vec ldv(const double* __restrict__ p) { return vec(p[0], p[1], p[2]); }
-GD_FN Bbox ldbb(const double* __restrict__ p) {
-    // bbox records are 16-byte aligned: three 16-byte loads
-    const double2* q = reinterpret_cast<const double2*>(p);
-    double2 a = gd_ldg(q), b = gd_ldg(q + 1), c = gd_ldg(q + 2);
+GD_FN Vec ldv(const Flt* __restrict__ p) { return vec(p[0], p[1], p[2]); }
+GD_FN Bbox ldbb(const Flt* __restrict__ p) {
+    // bbox records are 16-byte aligned (FP64): three 16-byte loads
+    const Flt2* q = reinterpret_cast<const Flt2*>(p);
+    Flt2 a = gd_ldg(q), b = gd_ldg(q + 1), c = gd_ldg(q + 2);
     return mkbb(vec(a.x, a.y, b.x), vec(b.y, c.x, c.y));
+}
+// order-preserving integer key of a non-negative depth (atomicMin on it) and back
+GD_FN unsigned long long flt_key(Flt x) {
+#if defined(__CUDA_ARCH__) && defined(GLOME_F32)
+    return (unsigned long long)__float_as_uint(x);
+#elif defined(__CUDA_ARCH__)
+    return (unsigned long long)__double_as_longlong(x);
+#else
+    unsigned long long w = 0; __builtin_memcpy(&w, &x, sizeof(x)); return w;
+#endif
+}
+GD_FN Flt key_flt(unsigned long long w) {
+#if defined(__CUDA_ARCH__) && defined(GLOME_F32)
+    return __uint_as_float((unsigned int)w);
+#elif defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)w);
+#else
+    Flt x; __builtin_memcpy(&x, &w, sizeof(x)); return x;
+#endif
+}
+// one BIH branch (BihBranch lsplit rsplit axis l r, Bih.hs:55-57)
+struct BihStep { Flt ls, rs; int axis, left, right; };
+GD_FN BihStep ld_bih(const DBihNode* __restrict__ base, int ref) {
+    BihStep b;
+#ifdef GLOME_F32
+    const int4 w = gd_ldg(reinterpret_cast<const int4*>(base + ref));
+    b.ls = key_flt((unsigned int)w.x); b.rs = key_flt((unsigned int)w.y); b.left = w.z; b.axis = w.w & 3; b.right = w.w >> 2;
+#else
+    const double2* np = reinterpret_cast<const double2*>(base + ref);  // 32-byte node: two 16-byte loads
+    const double2 sp2 = gd_ldg(np);
+    const int4 ii = gd_ldg(reinterpret_cast<const int4*>(np + 1));
+    b.ls = sp2.x; b.rs = sp2.y; b.axis = ii.x; b.left = ii.y; b.right = ii.z;
+#endif
+    return b;
+}
+// one Mesh BVH branch (Branch lbb rbb l r, Mesh.hs:36)
+GD_FN void ld_bvh(const DBvhNode* __restrict__ base, int ref, Bbox& lbb, Bbox& rbb, int& left, int& right) {
+    const Flt2* np = reinterpret_cast<const Flt2*>(base + ref);
+    const Flt2 l0 = gd_ldg(np), l1 = gd_ldg(np + 1), l2 = gd_ldg(np + 2);
+    const Flt2 r0 = gd_ldg(np + 3), r1 = gd_ldg(np + 4), r2 = gd_ldg(np + 5);
+    const int2 kids = gd_ldg(reinterpret_cast<const int2*>(np + 6));
+    lbb = mkbb(vec(l0.x, l0.y, l1.x), vec(l1.y, l2.x, l2.y));
+    rbb = mkbb(vec(r0.x, r0.y, r1.x), vec(r1.y, r2.x, r2.y));
+    left = kids.x; right = kids.y;
 }
 
 // ---------------------------------------------------------------------------------------------
 // primitives.  FULL = also produce position and normal.
 // ---------------------------------------------------------------------------------------------
 template <bool FULL>
-GD_FN bool prim_sphere(const double* __restrict__ p, const Ray& ray, Flt dist, Flt& t, Vec& pos,
+GD_FN bool prim_sphere(const Flt* __restrict__ p, const Ray& ray, Flt dist, Flt& t, Vec& pos,
                                             Vec& n) {
     // Sphere.hs:20-41.  {cx,cy,cz,r} is 32-byte aligned: two 16-byte loads
-    const double2* q = reinterpret_cast<const double2*>(p);
-    double2 c01 = gd_ldg(q), c23 = gd_ldg(q + 1);
+    const Flt2* q = reinterpret_cast<const Flt2*>(p);
+    Flt2 c01 = gd_ldg(q), c23 = gd_ldg(q + 1);
     Vec center = vec(c01.x, c01.y, c23.x);
     Flt r = c23.y;
     Vec eo = vsub(center, ray.o);
@@ -139,7 +198,7 @@ GD_FN bool prim_sphere(const double* __restrict__ p, const Ray& ray, Flt dist, F
     Flt csqr = vdot(eo, eo);
     Flt rsqr = r * r;
     Flt disc = rsqr - (csqr - vsqr);
-    if (disc < 0.0) return false;
+    if (disc < 0) return false;
     Flt d = sqrt(disc);
     Flt hitdist = ((v - d) > 0) ? (v - d) : (v + d);
     if ((hitdist < 0) || (hitdist > dist)) return false;
@@ -150,20 +209,20 @@ GD_FN bool prim_sphere(const double* __restrict__ p, const Ray& ray, Flt dist, F
     }
     return true;
 }
-GD_FN bool shadow_sphere(const double* __restrict__ p, const Ray& ray, Flt dist) {
+GD_FN bool shadow_sphere(const Flt* __restrict__ p, const Ray& ray, Flt dist) {
     // Sphere.hs:51-71
-    const double2* q = reinterpret_cast<const double2*>(p);
-    double2 c01 = gd_ldg(q), c23 = gd_ldg(q + 1);
+    const Flt2* q = reinterpret_cast<const Flt2*>(p);
+    Flt2 c01 = gd_ldg(q), c23 = gd_ldg(q + 1);
     Vec center = vec(c01.x, c01.y, c23.x);
     Flt r = c23.y;
     Vec eo = vsub(center, ray.o);
     Flt v = vdot(eo, ray.d);
-    if ((dist >= (v - r)) && (v > 0.0)) {
+    if ((dist >= (v - r)) && (v > 0)) {
         Flt vsqr = v * v;
         Flt csqr = vdot(eo, eo);
         Flt rsqr = r * r;
         Flt disc = rsqr - (csqr - vsqr);
-        if (disc < 0.0) return false;
+        if (disc < 0) return false;
         Flt d = sqrt(disc);
         Flt hitdist = ((v - d) > 0) ? (v - d) : (v + d);
         if ((hitdist < 0) || (hitdist > dist)) return false;
@@ -182,7 +241,7 @@ GD_FN bool prim_triangle(const Vec& p1, const Vec& p2, const Vec& p3, bool smoot
     Vec s1 = vcross(ray.d, e2);
     Flt divisor = vdot(s1, e1);
     if (divisor == 0) return false;
-    Flt invdivisor = 1.0 / divisor;
+    Flt invdivisor = FL(1.0) / divisor;
     Vec d = vsub(ray.o, p1);
     Flt b1 = vdot(d, s1) * invdivisor;
     if (b1 < 0 || b1 > 1) return false;
@@ -212,7 +271,7 @@ GD_FN bool shadow_triangle(const Vec& p1, const Vec& p2, const Vec& p3, const Ra
     Vec s1 = vcross(ray.d, e2);
     Flt divisor = vdot(s1, e1);
     if (divisor == 0) return false;
-    Flt invdivisor = 1.0 / divisor;
+    Flt invdivisor = FL(1.0) / divisor;
     Vec d = vsub(ray.o, p1);
     Flt b1 = vdot(d, s1) * invdivisor;
     if ((b1 < 0) || (b1 > 1)) return false;
@@ -224,7 +283,7 @@ GD_FN bool shadow_triangle(const Vec& p1, const Vec& p2, const Vec& p3, const Ra
 }
 
 template <bool FULL>
-GD_FN bool prim_box(const double* __restrict__ p, const Ray& r, Flt d, Flt& t, Vec& pos, Vec& n) {
+GD_FN bool prim_box(const Flt* __restrict__ p, const Ray& r, Flt d, Flt& t, Vec& pos, Vec& n) {
     // Box.hs:18-54
     Bbox b = ldbb(p);
     Flt dx = r.d.x, dy = r.d.y, dz = r.d.z;
@@ -258,7 +317,7 @@ GD_FN bool prim_box(const double* __restrict__ p, const Ray& r, Flt d, Flt& t, V
 // the same, with 1/d handed in: the three quotients depend on the ray only, so a caller testing many boxes with one ray
 // (a group of boxes, a BIH) computes them once.  Bit-identical to prim_box.
 template <bool FULL>
-GD_FN bool prim_box_rcp(const double* __restrict__ p, const Ray& r, Flt dxrcp, Flt dyrcp, Flt dzrcp, Flt d, Flt& t, Vec& pos, Vec& n) {
+GD_FN bool prim_box_rcp(const Flt* __restrict__ p, const Ray& r, Flt dxrcp, Flt dyrcp, Flt dzrcp, Flt d, Flt& t, Vec& pos, Vec& n) {
     Bbox b = ldbb(p);
     Flt dx = r.d.x, dy = r.d.y, dz = r.d.z;
     Flt inx, outx, iny, outy, inz, outz;
@@ -296,14 +355,14 @@ GD_FN void bbclip_ub_pre(const Ray& r, Flt dxrcp, Flt dyrcp, Flt dzrcp, const Bb
     near_ = fmax3(inx, iny, inz);
     far_ = fmin3(outx, outy, outz);
 }
-GD_FN bool shadow_box_rcp(const double* __restrict__ p, const Ray& r, Flt dxrcp, Flt dyrcp, Flt dzrcp, Flt d) {  // Box.hs:56-62
+GD_FN bool shadow_box_rcp(const Flt* __restrict__ p, const Ray& r, Flt dxrcp, Flt dyrcp, Flt dzrcp, Flt d) {  // Box.hs:56-62
     Bbox b = ldbb(p);
     Flt near_, far_;
     bbclip_ub_pre(r, dxrcp, dyrcp, dzrcp, b, near_, far_);
     if ((near_ > far_) || far_ <= 0 || far_ > d) return false;
     return true;
 }
-GD_FN bool shadow_box(const double* __restrict__ p, const Ray& r, Flt d) {  // Box.hs:56-62
+GD_FN bool shadow_box(const Flt* __restrict__ p, const Ray& r, Flt d) {  // Box.hs:56-62
     Bbox b = ldbb(p);
     Flt near_, far_;
     bbclip_ub(r, b, near_, far_);
@@ -312,7 +371,7 @@ GD_FN bool shadow_box(const double* __restrict__ p, const Ray& r, Flt d) {  // B
 }
 
 template <bool FULL>
-GD_FN bool prim_plane(const double* __restrict__ p, const Ray& ray, Flt d, Flt& t, Vec& pos, Vec& n) {
+GD_FN bool prim_plane(const Flt* __restrict__ p, const Ray& ray, Flt d, Flt& t, Vec& pos, Vec& n) {
     // Plane.hs:27-32
     Vec norm = ldv(p);
     Flt offset = p[3];
@@ -338,7 +397,7 @@ GD_FN bool prim_disc_v(const Vec& point, const Vec& norm, Flt radius_sqr, const 
 }
 
 template <bool FULL>
-GD_FN bool prim_cylinder(const double* __restrict__ p, const Ray& ray, Flt d, Flt& t, Vec& pos, Vec& n) {
+GD_FN bool prim_cylinder(const Flt* __restrict__ p, const Ray& ray, Flt d, Flt& t, Vec& pos, Vec& n) {
     // Cone.hs:104-139
     Flt r = p[0], h1 = p[1], h2 = p[2];
     Flt ox = ray.o.x, oy = ray.o.y, oz = ray.o.z, dx = ray.d.x, dy = ray.d.y, dz = ray.d.z;
@@ -348,7 +407,7 @@ GD_FN bool prim_cylinder(const double* __restrict__ p, const Ray& ray, Flt d, Fl
     Flt disc = b * b - 4 * a * c;
     if (disc < 0) return false;
     Flt discsqrt = sqrt(disc);
-    Flt q = (b < 0) ? (b - discsqrt) * (-0.5) : (b + discsqrt) * (-0.5);
+    Flt q = (b < 0) ? (b - discsqrt) * FL(-0.5) : (b + discsqrt) * FL(-0.5);
     Flt t0p = q / a;
     Flt t1p = c / q;
     Flt t0 = fmin_(t0p, t1p);
@@ -372,7 +431,7 @@ GD_FN bool prim_cylinder(const double* __restrict__ p, const Ray& ray, Flt d, Fl
 
 // rayint_cone (Cone.hs:155-204) and shadow_cone (Cone.hs:206-245) share everything but the result
 template <bool FULL>
-GD_FN bool prim_cone(const double* __restrict__ p, const Ray& ray, Flt d, Flt& t, Vec& pos, Vec& n) {
+GD_FN bool prim_cone(const Flt* __restrict__ p, const Ray& ray, Flt d, Flt& t, Vec& pos, Vec& n) {
     Flt r = p[0], clip1 = p[1], clip2 = p[2], height = p[3];
     Flt ox = ray.o.x, oy = ray.o.y, oz = ray.o.z, dx = ray.d.x, dy = ray.d.y, dz = ray.d.z;
     Flt kp = r / height;
@@ -383,7 +442,7 @@ GD_FN bool prim_cone(const double* __restrict__ p, const Ray& ray, Flt d, Flt& t
     Flt disc = b * b - 4 * a * c;
     if (disc < 0) return false;
     Flt discsqrt = sqrt(disc);
-    Flt q = (b < 0) ? (b - discsqrt) * (-0.5) : (b + discsqrt) * (-0.5);
+    Flt q = (b < 0) ? (b - discsqrt) * FL(-0.5) : (b + discsqrt) * FL(-0.5);
     Flt t0p = q / a;
     Flt t1p = c / q;
     Flt t0 = fmin_(t0p, t1p);
@@ -422,7 +481,7 @@ GD_FN bool is_prim(int type) { return type >= GLOME_SPHERE && type <= GLOME_CONE
 template <bool FULL>
 GD_FN bool prim_rayint(const DScene& S, const GlomeNode& nd, const Ray& r, Flt d, Flt& t, Vec& pos,
                                             Vec& n) {
-    const double* p = S.dpool + nd.a;
+    const Flt* p = S.dpool + nd.a;
     switch (nd.type) {
         case GLOME_SPHERE: return prim_sphere<FULL>(p, r, d, t, pos, n);
         case GLOME_TRIANGLE: {
@@ -442,7 +501,7 @@ GD_FN bool prim_rayint(const DScene& S, const GlomeNode& nd, const Ray& r, Flt d
 }
 // shadow of a primitive node (default = rayint hit, Solid.hs:218-221)
 GD_FN bool prim_shadow(const DScene& S, const GlomeNode& nd, const Ray& r, Flt d) {
-    const double* p = S.dpool + nd.a;
+    const Flt* p = S.dpool + nd.a;
     Flt t;
     Vec a, b;
     switch (nd.type) {
@@ -458,7 +517,7 @@ GD_FN bool prim_shadow(const DScene& S, const GlomeNode& nd, const Ray& r, Flt d
     return false;
 }
 GD_FN bool prim_inside(const DScene& S, const GlomeNode& nd, const Vec& pt) {
-    const double* p = S.dpool + nd.a;
+    const Flt* p = S.dpool + nd.a;
     switch (nd.type) {
         case GLOME_SPHERE: {  // Sphere.hs:73-76
             Vec offset = vsub(ldv(p), pt);
@@ -544,9 +603,9 @@ GD_FN void rayint_bih(const DScene& S, const GlomeNode& nd, const Ray& r, Flt d,
         } else {
             // 32-byte node: two 16-byte loads
             if (cnt) cnt->bih++;
-            const double2* np = reinterpret_cast<const double2*>(S.bih + ref);
-            double2 sp2 = gd_ldg(np);
-            int4 ii = gd_ldg(reinterpret_cast<const int4*>(np + 1));
+            const BihStep bs_ = ld_bih(S.bih, ref);
+            const Flt2 sp2 = {bs_.ls, bs_.rs};
+            int4 ii; ii.x = bs_.axis; ii.y = bs_.left; ii.z = bs_.right; ii.w = 0;
             int axis = ii.x;
             Flt dr_ = dirr[axis], o = org[axis];
             Flt dl = (sp2.x - o) * dr_;
@@ -620,9 +679,9 @@ GD_FN bool shadow_bih(const DScene& S, const GlomeNode& nd, const Ray& r, Flt d,
             pop = true;
         } else {
             if (cnt) cnt->bih++;
-            const double2* np = reinterpret_cast<const double2*>(S.bih + ref);
-            double2 sp2 = gd_ldg(np);
-            int4 ii = gd_ldg(reinterpret_cast<const int4*>(np + 1));
+            const BihStep bs_ = ld_bih(S.bih, ref);
+            const Flt2 sp2 = {bs_.ls, bs_.rs};
+            int4 ii; ii.x = bs_.axis; ii.y = bs_.left; ii.z = bs_.right; ii.w = 0;
             int axis = ii.x;
             Flt dr_ = dirr[axis], o = org[axis];
             Flt dl = (sp2.x - o) * dr_;
@@ -705,12 +764,9 @@ GD_FN void rayint_mesh(const DScene& S, int ni, const GlomeNode& nd, const Ray& 
         } else {
             // 128-byte node: two boxes + two child refs
             if (cnt) cnt->bvh++;
-            const double2* np = reinterpret_cast<const double2*>(S.bvh + ref);
-            double2 l0 = gd_ldg(np), l1 = gd_ldg(np + 1), l2 = gd_ldg(np + 2);
-            double2 r0 = gd_ldg(np + 3), r1 = gd_ldg(np + 4), r2 = gd_ldg(np + 5);
-            int2 kids = gd_ldg(reinterpret_cast<const int2*>(np + 6));
-            Bbox lbb = mkbb(vec(l0.x, l0.y, l1.x), vec(l1.y, l2.x, l2.y));
-            Bbox rbb = mkbb(vec(r0.x, r0.y, r1.x), vec(r1.y, r2.x, r2.y));
+            Bbox lbb, rbb;
+            int2 kids;
+            ld_bvh(S.bvh, ref, lbb, rbb, kids.x, kids.y);
             Flt lnearp, lfarp, rnearp, rfarp;
             bbclip_ub_rcp(ray.o, rcp, lbb, lnearp, lfarp);
             bbclip_ub_rcp(ray.o, rcp, rbb, rnearp, rfarp);
@@ -825,7 +881,7 @@ GD_FN void finalize_flat(const DScene& S, const Ray& r, Hit& h) {
     if (!h.hit) return;
     GlomeNode nd = S.nodes[h.prim];
     Flt t; Vec pos, n;
-    const Flt big = 1.0e300;
+    const Flt big = GLM_BIG;
     if (nd.type == GLOME_MESH) {
         const GlomeMeshHeader* mh = reinterpret_cast<const GlomeMeshHeader*>(S.ipool + nd.a);
         const int32_t* T = S.ipool + mh->tris_off + 8 * h.sub;
@@ -840,8 +896,27 @@ GD_FN void finalize_flat(const DScene& S, const Ray& r, Hit& h) {
             cn = ldv(S.dpool + mh->norms_off + 3 * T[5]);
         }
         prim_triangle<true>(a, b, c, smooth, an, bn, cn, r, big, t, pos, n);
+#ifdef GLOME_F32
+        if (h.t > 1) {  // (see below)
+            const Ray r2 = mkray(vscaleadd(r.o, r.d, h.t - 1), r.d);
+            Flt t2; Vec p2, n2;
+            if (prim_triangle<true>(a, b, c, smooth, an, bn, cn, r2, big, t2, p2, n2)) { pos = p2; n = n2; }
+        }
+#endif
     } else {
         prim_rayint<true>(S, nd, r, big, t, pos, n);
+#ifdef GLOME_F32
+        // FP32 only.  A depth of a few hundred units carries an error of a few float ulps of t -- about the reference's
+        // delta (1e-4, Vec.hs:40), which is what lifts a shadow ray off the surface it starts on (Shader.hs:76): the point
+        // would land inside its own primitive on a good share of the pixels ("shadow acne" that the Double reference does
+        // not have).  The winner is therefore intersected once more from one unit in front of the hit, where the same
+        // test resolves the surface to ~1e-7; the depth that took part in the nearest-hit fold stays as it was.
+        if (h.t > 1) {
+            const Ray r2 = mkray(vscaleadd(r.o, r.d, h.t - 1), r.d);
+            Flt t2; Vec p2, n2;
+            if (prim_rayint<true>(S, nd, r2, big, t2, p2, n2)) { pos = p2; n = n2; }
+        }
+#endif
     }
     h.pos = pos; h.norm = n; h.ray = r;
 }
@@ -875,7 +950,7 @@ GD_FN ColorA cafold(const ColorA& x, const ColorA& y) {  // Clr.hs:106
 }
 GD_FN Flt triangle_wave(Flt x) {  // Texture.hs:16
     Flt offset = x - floor(x);
-    return (offset < 0.5) ? (offset * 2) : (2 - (offset * 2));
+    return (offset < FL(0.5)) ? (offset * 2) : (2 - (offset * 2));
 }
 GD_FN Flt omega(Flt t_) {  // Texture.hs:49
     Flt t = fabs_(t_);
@@ -989,7 +1064,7 @@ GD_FN void eval_texture(const DScene& S, int tex, const Vec& pos, MatVal& m, uns
     Flt scale;
     if (kind == GLOME_TEX_STRIPE_BLEND) scale = triangle_wave(vdot(pos, vec(T->p[0], T->p[1], T->p[2])));  // TestScene.hs:225
     else {  // perlin (Texture.hs:109-116); out-of-range results are counted, not trapped
-        scale = (noise(vscale(pos, T->p[0])) + 1) * 0.5;
+        scale = (noise(vscale(pos, (Flt)T->p[0])) + 1) * FL(0.5);
         if (scale > 1 || scale < 0) perlin_range++;
     }
     m.kind = GLOME_MAT_BLEND; m.a = T->a; m.b = T->b; m.c = 0; m.d = 0;
@@ -1018,8 +1093,11 @@ GD_FN void mshade_flat(const DScene& S, const LightSel& L, const MatVal& m, cons
     if (m.kind == GLOME_MAT_SURFACE) shade_surface(S, L, ri.pos, m.p, ri.norm, eyedir, outc);
     else if (m.kind == GLOME_MAT_BLEND) {  // Shader.hs:181-184
         ColorA ca, cb;
-        shade_surface(S, L, ri.pos, S.materials[m.a].p, ri.norm, eyedir, ca);
-        shade_surface(S, L, ri.pos, S.materials[m.b].p, ri.norm, eyedir, cb);
+        MatVal ma, mb;  // (the payloads in the working precision)
+        mat_load(S, m.a, ma);
+        mat_load(S, m.b, mb);
+        shade_surface(S, L, ri.pos, ma.p, ri.norm, eyedir, ca);
+        shade_surface(S, L, ri.pos, mb.p, ri.norm, eyedir, cb);
         outc = caweight(ca, cb, m.p[0]);
     } else outc = mkca(0, 0, 0, 0);
 }

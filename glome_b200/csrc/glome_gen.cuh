@@ -128,7 +128,7 @@ GD_NOINLINE bool gq_inside(const DScene& S, int root, const Vec& pt0, int* ovf) 
                     n = nd.a;
                     break;
                 case GLOME_BIH: {          // Bih.hs:550-565: strict box test, then the point descent
-                    const double* b = S.dpool + nd.b;
+                    const Flt* b = S.dpool + nd.b;
                     if ((pt.x > b[0]) && (pt.x < b[3]) && (pt.y > b[1]) && (pt.y < b[4]) && (pt.z > b[2]) && (pt.z < b[5])) {
                         bref = nd.a; mode = 1;
                     } else { v = false; mode = 2; }
@@ -159,9 +159,10 @@ GD_NOINLINE bool gq_inside(const DScene& S, int root, const Vec& pt0, int* ovf) 
                 n = first; mode = 0;
                 continue;
             }
-            const GlomeBihNode* bn = S.bih + bref;
+            const BihStep bs_ = ld_bih(S.bih, bref);
+            const BihStep* bn = &bs_;
             const Flt o = va(pt, bn->axis);
-            const bool gl = o < bn->lsplit, gr = o > bn->rsplit;
+            const bool gl = o < bn->ls, gr = o > bn->rs;
             if (gl && gr) {
                 if (fp >= GI_FRAMES) { *ovf = 1; return false; }
                 fk[fp] = GI_BIH_R; fa[fp] = bn->right; fb[fp] = 0; fp++;
@@ -259,10 +260,11 @@ GD_NOINLINE void gq_metainfo(const DScene& S, int root, const Vec& v, PStk& texs
                 if (cnt > 0) GM_PUSH(GM_LIST_DESC, first, first + cnt - 1, p);
                 continue;
             }
-            const GlomeBihNode* bn = S.bih + a;
+            const BihStep bs_ = ld_bih(S.bih, a);
+            const BihStep* bn = &bs_;
             const Flt o = va(pt, bn->axis);
-            if (o > bn->rsplit) GM_PUSH(GM_BIHREF, bn->right, 0, p);  // left part ++ right part: left is popped first
-            if (o < bn->lsplit) GM_PUSH(GM_BIHREF, bn->left, 0, p);
+            if (o > bn->rs) GM_PUSH(GM_BIHREF, bn->right, 0, p);  // left part ++ right part: left is popped first
+            if (o < bn->ls) GM_PUSH(GM_BIHREF, bn->left, 0, p);
             continue;
         }
         const GlomeNode nd = S.nodes[a];
@@ -278,7 +280,7 @@ GD_NOINLINE void gq_metainfo(const DScene& S, int root, const Vec& v, PStk& texs
                 np++;
                 break;
             case GLOME_BIH: {  // Bih.hs:579-585
-                const double* bb = S.dpool + nd.b;
+                const Flt* bb = S.dpool + nd.b;
                 if ((pt.x > bb[0]) && (pt.x < bb[3]) && (pt.y > bb[1]) && (pt.y < bb[4]) && (pt.z > bb[2]) && (pt.z < bb[5]))
                     GM_PUSH(GM_BIHREF, nd.a, 0, p);
                 break;
@@ -354,20 +356,8 @@ GD_FN unsigned long long gq_hdr(int op, int a, int b) {
 GD_FN int gq_op(unsigned long long h) { return (int)(h & 0xff); }
 GD_FN int gq_a(unsigned long long h) { return ((int)(((unsigned int)(h >> 8)) << 4)) >> 4; }   // sign-extended 28 bits
 GD_FN int gq_b(unsigned long long h) { return ((int)(((unsigned int)(h >> 36)) << 4)) >> 4; }
-GD_FN unsigned long long gq_d2w(Flt x) {
-#if defined(__CUDA_ARCH__)
-    return (unsigned long long)__double_as_longlong(x);
-#else
-    unsigned long long w; __builtin_memcpy(&w, &x, 8); return w;
-#endif
-}
-GD_FN Flt gq_w2d(unsigned long long w) {
-#if defined(__CUDA_ARCH__)
-    return __longlong_as_double((long long)w);
-#else
-    Flt x; __builtin_memcpy(&x, &w, 8); return x;
-#endif
-}
+GD_FN unsigned long long gq_d2w(Flt x) { return flt_key(x); }  // the bits of a Flt in a control-stack word (any sign)
+GD_FN Flt gq_w2d(unsigned long long w) { return key_flt(w); }
 
 enum { GS_ENTER = 0, GS_BRANCH, GS_LIST, GS_RET, GS_DONE };
 
@@ -381,7 +371,7 @@ enum { GI_DEAD = 0, GI_PRIM = 1, GI_INST_PRIM = 2, GI_COMPLEX = 3 };
 // once per ray by the caller (only the box uses it).
 GD_FN bool gq_prim_rayint(const DScene& S, int type, int payload, const Ray& r, Flt rx, Flt ry, Flt rz, Flt d, Flt& t, Vec& pos,
                           Vec& n) {
-    const double* p = S.dpool + payload;
+    const Flt* p = S.dpool + payload;
     switch (type) {
         case GLOME_SPHERE: return prim_sphere<true>(p, r, d, t, pos, n);
         case GLOME_TRIANGLE: {
@@ -402,7 +392,7 @@ GD_FN bool gq_prim_rayint(const DScene& S, int type, int payload, const Ray& r, 
 // back on rayint's hit flag (Solid.hs:218-221; shadow_cone, Cone.hs:206-245, is rayint_cone's hit test)
 GD_FN bool gq_has_shadow_method(int type) { return type <= GLOME_BOX; }
 GD_FN bool gq_prim_shadow(const DScene& S, int type, int payload, const Ray& r, Flt rx, Flt ry, Flt rz, Flt d) {
-    const double* p = S.dpool + payload;
+    const Flt* p = S.dpool + payload;
     switch (type) {
         case GLOME_SPHERE: return shadow_sphere(p, r, d);
         case GLOME_TRIANGLE:
@@ -573,9 +563,9 @@ GD_FN void qvm_step(const DScene& S, QRegs& q, QVM& vm, GCnt& cnt) {
     // ---------------- BRANCH: BIH nodes (Bih.hs:340-366 / 516-542) ----------------
     while (st == GS_BRANCH) {
         cnt.bih++;
-        const double2* np_ = reinterpret_cast<const double2*>(S.bih + ref);
-        const double2 sp2 = gd_ldg(np_);
-        const int4 ii = gd_ldg(reinterpret_cast<const int4*>(np_ + 1));
+        const BihStep bs_ = ld_bih(S.bih, ref);
+        const Flt2 sp2 = {bs_.ls, bs_.rs};
+        int4 ii; ii.x = bs_.axis; ii.y = bs_.left; ii.z = bs_.right; ii.w = 0;
         const Flt dr_ = (ii.x == 0) ? drx : ((ii.x == 1) ? dry : drz);
         const Flt o = (ii.x == 0) ? r.o.x : ((ii.x == 1) ? r.o.y : r.o.z);
         const Flt dl = (sp2.x - o) * dr_;
@@ -607,7 +597,7 @@ GD_FN void qvm_step(const DScene& S, QRegs& q, QVM& vm, GCnt& cnt) {
         const int item = li++;
         if (llin) {  // bare sphere of a linear block: no record to chase
             cnt.prim++;
-            const double* sph = S.dpool + lin_a0 + 4 * (item - lin_j0);
+            const Flt* sph = S.dpool + lin_a0 + 4 * (item - lin_j0);
             if (smode) {
                 if (shadow_sphere(sph, r, ld)) { retb = true; st = GS_RET; }
             } else {
@@ -1254,7 +1244,8 @@ GD_NOINLINE int gq_debug_count(const DScene& S, QVM& vm, int root, const Ray& ra
                         total++;
                         if (near_ > far_) pop = true;  // (RayMiss,0) wrapped with 1: only possible at the root
                         else {
-                            const GlomeBihNode bn = S.bih[ref];
+                            const BihStep bs_ = ld_bih(S.bih, ref);
+                            struct { Flt lsplit, rsplit; int axis, left, right; } bn = {bs_.ls, bs_.rs, bs_.axis, bs_.left, bs_.right};
                             const Flt dr_ = (bn.axis == 0) ? drx : ((bn.axis == 1) ? dry : drz);
                             const Flt o = (bn.axis == 0) ? r.o.x : ((bn.axis == 1) ? r.o.y : r.o.z);
                             const Flt dl = (bn.lsplit - o) * dr_;

@@ -17,10 +17,17 @@
 
 namespace glm {
 
+// Vec.hs:7-9: `type Flt = Double`, with the note "make separate Float and Double instances of this library".
+// GLOME_F32 (device translation unit glome_cuda_f32.cu only) is that Float instance: the optional FP32 mode.
+#ifdef GLOME_F32
+typedef float Flt;
+#else
 typedef double Flt;  // Vec.hs:9
+#endif
 
-#define GLM_INFINITY 1000000.0  /* Vec.hs:14: not IEEE inf */
-#define GLM_DELTA 0.0001        /* Vec.hs:40 */
+#define FL(x) ((glm::Flt)(x))         /* a literal of the working precision (no silent promotion to double) */
+#define GLM_INFINITY FL(1000000.0)  /* Vec.hs:14: not IEEE inf */
+#define GLM_DELTA FL(0.0001)        /* Vec.hs:40 */
 
 GLM_HD Flt fmin_(Flt a, Flt b) { return a > b ? b : a; }  // Vec.hs:44
 GLM_HD Flt fmax_(Flt a, Flt b) { return a > b ? a : b; }  // Vec.hs:48
@@ -58,7 +65,7 @@ GLM_HD Vec vscaleadd(const Vec& a, const Vec& b, Flt f) {                       
     return vec(a.x + (b.x * f), a.y + (b.y * f), a.z + (b.z * f));
 }
 GLM_HD Vec vnorm(const Vec& a) {                                                                   // Vec.hs:314
-    Flt invlen = 1.0 / sqrt((a.x * a.x) + (a.y * a.y) + (a.z * a.z));
+    Flt invlen = FL(1.0) / sqrt((a.x * a.x) + (a.y * a.y) + (a.z * a.z));
     return vec(a.x * invlen, a.y * invlen, a.z * invlen);
 }
 GLM_HD Vec bisect(const Vec& a, const Vec& b) { return vnorm(vadd(a, b)); }                        // Vec.hs:331
@@ -108,7 +115,7 @@ GLM_HD Bbox empty_bbox() {                                                      
 GLM_HD Bbox everything_bbox() {                                                                    // Vec.hs:712
     return mkbb(vec(-GLM_INFINITY, -GLM_INFINITY, -GLM_INFINITY), vec(GLM_INFINITY, GLM_INFINITY, GLM_INFINITY));
 }
-GLM_HD Vec bbmid(const Bbox& b) { return vscale(vadd(b.p1, b.p2), 0.5); }                          // Bih.hs:162
+GLM_HD Vec bbmid(const Bbox& b) { return vscale(vadd(b.p1, b.p2), FL(0.5)); }                          // Bih.hs:162
 
 // one slab of bbclip_ub / bbclip_ub_rcp: `pos` is the sign test the caller chose
 GLM_HD void slab(bool pos, Flt p1, Flt p2, Flt o, Flt rcp, Flt& in, Flt& out) {

@@ -49,12 +49,12 @@ struct WaveParams {
     const int* queue;
     const int* queue_count;
     // per-sample state
-    double* hit_t;
+    Flt* hit_t;
     int* hit_seg;
     int* hit_item;
     int* hit_sub;
     int* hit_flags;
-    double* surf;            // pos(3), norm(3) per sample
+    Flt* surf;               // pos(3), norm(3) per sample
     unsigned int* occl;      // bit li = light li is occluded
     int2* squeue;            // shadow queue {sample, light}
     int* squeue_count;
@@ -85,7 +85,7 @@ __device__ __forceinline__ bool sample_pixel(const WaveParams& P, long long s, i
 }
 __device__ __forceinline__ Ray sample_ray(const WaveParams& P, int x, int y) {
     Flt xc, yc;
-    if (P.mode == 5) getCoordsf(P.g.width, P.g.height, (Flt)x + 0.5, (Flt)y + 0.5, xc, yc);
+    if (P.mode == 5) getCoordsf(P.g.width, P.g.height, (Flt)x + FL(0.5), (Flt)y + FL(0.5), xc, yc);
     else getCoordsf(P.g.width, P.g.height, (Flt)x, (Flt)y, xc, yc);
     return camera_ray(P.cam, xc, yc);
 }
@@ -108,7 +108,7 @@ __device__ __forceinline__ void wave_flush(unsigned long long* st, const unsigne
 // stats slots: 0 primary 1 shadow 2 secondary 3 overflow 4 perlin_range 5 bih 6 prim 7 bvh 8 tri
 
 // shadow-ray of light li for the surface point of sample s (Shader.hs:70-78); same arithmetic as mpreshade
-__device__ __forceinline__ bool light_ray(const DScene& S, const double* surf, int li, Ray& r, Flt& d, Vec& ldir, Flt& llen,
+__device__ __forceinline__ bool light_ray(const DScene& S, const Flt* surf, int li, Ray& r, Flt& d, Vec& ldir, Flt& llen,
                                           bool& need_shadow) {
     const GlomeLight* Lp = S.lights + li;
     Vec pos = vec(surf[0], surf[1], surf[2]), norm = vec(surf[3], surf[4], surf[5]);
@@ -299,8 +299,8 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScen
         // order (solo), and that result is the one written.
         // members of a group share their nearest depth every round, so that a subtree behind a neighbour's hit is culled
         if (!ANY && nomore && active && light >= 0) {
-            if (has) atomicMin(&g_cull[gb + light], (unsigned long long)__double_as_longlong(best_t));
-            const Flt c = __longlong_as_double((long long)g_cull[gb + light]);
+            if (has) atomicMin(&g_cull[gb + light], flt_key(best_t));
+            const Flt c = key_flt(g_cull[gb + light]);
             if (c < best_t) { best_t = c; has = true; best_item = -1; }  // own hit is dominated: drop it
         }
         if (nomore && idle) {
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScen
                             g_t[gb + lane] = GLM_INFINITY; g_item[gb + lane] = -1; g_ovf[gb + lane] = 0; g_s[gb + lane] = s;
                             g_tie[gb + lane] = 0;
                             g_pend[gb + lane] = 1;
-                            g_cull[gb + lane] = (unsigned long long)__double_as_longlong(has ? best_t : (Flt)GLM_INFINITY);
+                            g_cull[gb + lane] = flt_key(has ? best_t : (Flt)GLM_INFINITY);
                         }
                     }
                 }
@@ -427,9 +427,9 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScen
 #ifndef GW_NOCOUNT
             n_bih++;
 #endif
-            const double2* np = reinterpret_cast<const double2*>(S.bih + ref);
-            double2 sp2 = __ldg(np);
-            int4 ii = __ldg(reinterpret_cast<const int4*>(np + 1));
+            const BihStep bs_ = ld_bih(S.bih, ref);
+            const Flt2 sp2 = {bs_.ls, bs_.rs};
+            int4 ii; ii.x = bs_.axis; ii.y = bs_.left; ii.z = bs_.right; ii.w = 0;
             Flt dr_ = (ii.x == 0) ? drx : ((ii.x == 1) ? dry : drz);
             Flt o = (ii.x == 0) ? r.o.x : ((ii.x == 1) ? r.o.y : r.o.z);
             Flt dl = (sp2.x - o) * dr_;
@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScen
 #ifndef GW_NOCOUNT
                     n_prim++;
 #endif
-                    const double* sph = S.dpool + a0 + 4 * (item - j0);
+                    const Flt* sph = S.dpool + a0 + 4 * (item - j0);
                     if (ANY) {
                         if (shadow_sphere(sph, r, dd)) { has = true; break; }
                     } else {
@@ -613,13 +613,12 @@ __global__ void __launch_bounds__(128, GW_BVH_MINBLOCKS) k_bvh_closest(DScene S,
         bool done = false;
         while (active && !done && ref >= 0) {
             n_bvh++;
-            const double2* np = reinterpret_cast<const double2*>(S.bvh + ref);
-            double2 l0 = __ldg(np), l1 = __ldg(np + 1), l2 = __ldg(np + 2);
-            double2 r0 = __ldg(np + 3), r1 = __ldg(np + 4), r2 = __ldg(np + 5);
-            int2 kids = __ldg(reinterpret_cast<const int2*>(np + 6));
+            Bbox lbb_, rbb_;
+            int2 kids;
+            ld_bvh(S.bvh, ref, lbb_, rbb_, kids.x, kids.y);
             Flt lnearp, lfarp, rnearp, rfarp;
-            bbclip_ub_rcp(r.o, rcp, mkbb(vec(l0.x, l0.y, l1.x), vec(l1.y, l2.x, l2.y)), lnearp, lfarp);
-            bbclip_ub_rcp(r.o, rcp, mkbb(vec(r0.x, r0.y, r1.x), vec(r1.y, r2.x, r2.y)), rnearp, rfarp);
+            bbclip_ub_rcp(r.o, rcp, lbb_, lnearp, lfarp);
+            bbclip_ub_rcp(r.o, rcp, rbb_, rnearp, rfarp);
             Flt lnear = hmax(near_, lnearp), lfar = hmin(far_, lfarp);
             Flt rnear = hmax(near_, rnearp), rfar = hmin(far_, rfarp);
             Flt best = has ? best_t : (Flt)GLM_INFINITY;
@@ -785,7 +784,7 @@ __device__ __forceinline__ void load_hit(const DScene& S, const WaveParams& P, c
     rebuild_stacks(S, segs, seg, P.hit_item[s], h.sub, h.tex, h.tag, h.prim, fl);
     h.flags |= fl;
     h.ray = r;
-    const double* sf = P.surf + 6 * s;
+    const Flt* sf = P.surf + 6 * s;
     h.pos = vec(sf[0], sf[1], sf[2]);
     h.norm = vec(sf[3], sf[4], sf[5]);
 }
@@ -816,7 +815,7 @@ __global__ void __launch_bounds__(128) k_surface(DScene S, WaveParams P, const S
                     rebuild_stacks(S, segs, seg, P.hit_item[s], h.sub, h.tex, h.tag, h.prim, fl);
                     if (fl) P.hit_flags[s] |= fl;
                     finalize_flat(S, r, h);
-                    double* sf = P.surf + 6 * s;
+                    Flt* sf = P.surf + 6 * s;
                     sf[0] = h.pos.x; sf[1] = h.pos.y; sf[2] = h.pos.z;
                     sf[3] = h.norm.x; sf[4] = h.norm.y; sf[5] = h.norm.z;
                     live = h.tex.n > 0;  // ctxb is only forced when a texture is shaded (Trace.hs:63)
@@ -910,11 +909,11 @@ __global__ void __launch_bounds__(128) k_shade(DScene S, WaveParams P, const Seg
             if (lastx && lasty) q = col;
             else {
                 TCw m;
-                if (lastx) { m.r = (a.r + b.r) * 0.5; m.g = (a.g + b.g) * 0.5; m.b = (a.b + b.b) * 0.5; m.a = (a.a + b.a) * 0.5; m.d = (a.d + b.d) * 0.5; }
-                else if (lasty) { m.r = (a.r + d.r) * 0.5; m.g = (a.g + d.g) * 0.5; m.b = (a.b + d.b) * 0.5; m.a = (a.a + d.a) * 0.5; m.d = (a.d + d.d) * 0.5; }
-                else { m.r = (a.r + b.r + c.r + d.r) * 0.25; m.g = (a.g + b.g + c.g + d.g) * 0.25; m.b = (a.b + b.b + c.b + d.b) * 0.25;
-                       m.a = (a.a + b.a + c.a + d.a) * 0.25; m.d = (a.d + b.d + c.d + d.d) * 0.25; }
-                q.r = (col.r + m.r) * 0.5; q.g = (col.g + m.g) * 0.5; q.b = (col.b + m.b) * 0.5; q.a = (col.a + m.a) * 0.5; q.d = (col.d + m.d) * 0.5;
+                if (lastx) { m.r = (a.r + b.r) * FL(0.5); m.g = (a.g + b.g) * FL(0.5); m.b = (a.b + b.b) * FL(0.5); m.a = (a.a + b.a) * FL(0.5); m.d = (a.d + b.d) * FL(0.5); }
+                else if (lasty) { m.r = (a.r + d.r) * FL(0.5); m.g = (a.g + d.g) * FL(0.5); m.b = (a.b + d.b) * FL(0.5); m.a = (a.a + d.a) * FL(0.5); m.d = (a.d + d.d) * FL(0.5); }
+                else { m.r = (a.r + b.r + c.r + d.r) * FL(0.25); m.g = (a.g + b.g + c.g + d.g) * FL(0.25); m.b = (a.b + b.b + c.b + d.b) * FL(0.25);
+                       m.a = (a.a + b.a + c.a + d.a) * FL(0.25); m.d = (a.d + b.d + c.d + d.d) * FL(0.25); }
+                q.r = (col.r + m.r) * FL(0.5); q.g = (col.g + m.g) * FL(0.5); q.b = (col.b + m.b) * FL(0.5); q.a = (col.a + m.a) * FL(0.5); q.d = (col.d + m.d) * FL(0.5);
             }
             col = q;
         } else if (P.mode == 0 && P.tint) {

@@ -458,12 +458,17 @@ class SceneBuilder:
 class Scene:
     """A FlatScene resident on one B200.  No CPU fallback: creation fails without a CUDA device."""
 
-    def __init__(self, flat, device=0):
+    def __init__(self, flat, device=0, precision=64):
+        """precision=32: the optional FP32 mode (Flt = Float, Vec.hs:7-9); everything else about the handle is the same."""
         self.lib = L.load()
         h = C.c_void_p()
-        L.check(self.lib.glome_scene_create(C.byref(flat), int(device), C.byref(h)))
+        if precision not in (32, 64):
+            raise ValueError("precision is 64 (the reference's Flt = Double) or 32")
+        create = self.lib.glome_scene_create if precision == 64 else self.lib.glome_scene_create_f32
+        L.check(create(C.byref(flat), int(device), C.byref(h)))
         self.h = h
         self.device = device
+        self.precision = precision
         self.scene_class = flat.scene_class
 
     def close(self):

@@ -256,6 +256,14 @@ int glome_device_count(void);
 /* scene flatten + upload, once; `desc` is copied. */
 int glome_scene_create(const GlomeFlatScene* desc, int device, GlomeScene** out);
 int glome_scene_destroy(GlomeScene* s);
+/* The optional FP32 mode (north_star; GlomeVec/Data/Glome/Vec.hs:7-9: `type Flt = Double` with the note "make separate
+ * Float and Double instances of this library"): the same scene evaluated with Flt = Float.  Payloads are rounded to float
+ * once, at upload (16-byte BIH nodes, 64-byte BVH nodes, 16-byte spheres); every kernel is the FP64 kernel's source
+ * compiled for float.  The handle is used with the ordinary entry points below (render, batches, pick); rays, cameras,
+ * frames and GlomeHit stay double at the boundary.  Results differ from FP64 within the FP32 tolerance the north_star
+ * states (RGB 1e-3 max abs away from silhouette pixels; tests/test_gpu_f32.py reports the id agreement rate).
+ * Not available through glome_multi_create (shard an FP32 scene with tile_first / tile_stride instead). */
+int glome_scene_create_f32(const GlomeFlatScene* desc, int device, GlomeScene** out);
 
 /* rayint sld ray d [] []  (Solid.hs:146-151).  rays = n*6 doubles {ox,oy,oz,dx,dy,dz};
  * tmax = n doubles, or 1 double when tmax_stride == 0. */
