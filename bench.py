@@ -244,8 +244,17 @@ def measure(X, cfg, steps, warmup, with_cpu, cpu_seconds, setup_report=False):
     for _ in range(warmup):
         rdr.render_frame_dev()
     barrier()
+    # The frame's ray count is the REFERENCE's: its adaptive schedule, passes 1-4 tracing only the samples their decisions
+    # ask for (GLOME_MODE_ADAPTIVE_AA_STRICT).  The timed frames may trace every pixel centre up front instead when that
+    # is faster on a rank (same frame bit for bit, more rays): those extra rays are never counted as work done.
+    if mode == L.MODE_ADAPTIVE_AA:
+        rdr.opts.mode = L.MODE_ADAPTIVE_AA_STRICT
     rdr.render_frame_dev(want_stats=True)
+    rdr.opts.mode = mode
     st = rdr.last_stats
+    for _ in range(4):  # let the schedule choice settle (each schedule is timed once before the faster one is kept)
+        rdr.render_frame_dev()
+        barrier()
     counts = torch.tensor([st.rays_primary, st.rays_shadow, st.rays_secondary, st.overflow_rays], dtype=torch.float64,
                           device="cuda")
     if world > 1:
@@ -279,7 +288,9 @@ def measure(X, cfg, steps, warmup, with_cpu, cpu_seconds, setup_report=False):
 
     # ---- the kernels of this rank's part of the frame, timed by CUDA events on the launching stream inside
     # glome_render_dev (per kernel family) ----
-    opts1 = G.render_opts(mode=mode, recurs=recurs, tile_first=rank, tile_stride=world)
+    # (for the roofline the reference schedule is timed: its visit counters and its kernel times belong together)
+    opts1 = G.render_opts(mode=L.MODE_ADAPTIVE_AA_STRICT if mode == L.MODE_ADAPTIVE_AA else mode, recurs=recurs,
+                          tile_first=rank, tile_stride=world)
     fam_ms = np.zeros(4)
     fam_n = np.zeros(4)
     kt = []

@@ -23,7 +23,7 @@ GLOME_MAX_STACK = 8
 NODE_TYPE_COUNT = 21
 
 CLASS_GENERAL, CLASS_FLAT = 0, 1
-MODE_ONE_RAY, MODE_ADAPTIVE_AA = 0, 1
+MODE_ONE_RAY, MODE_ADAPTIVE_AA, MODE_ADAPTIVE_AA_STRICT = 0, 1, 2
 
 OK, EINVAL, ECUDA, ENODEV, ELIMIT, EBUILD = 0, -1, -2, -3, -4, -5
 HITFLAG_STACK_OVERFLOW, HITFLAG_CSG_OVERFLOW = 1, 2

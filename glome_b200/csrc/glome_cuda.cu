@@ -679,6 +679,12 @@ struct GlomeScene {  // (global scope: the C-ABI's opaque handle)
     cudaEvent_t aa_ev;
     bool aa_valid;
     int aa_w, aa_h, aa_first, aa_stride, aa_bs;
+    // ... and which of the two schedules (0 = adaptive passes, 1 = speculated centres) is faster for this geometry on this
+    // device: each is timed with its own event pair, harvested without a host sync when a later frame starts
+    cudaEvent_t aa_t0[2], aa_t1[2];
+    bool aa_pending[2], aa_ms_valid[2];
+    float aa_ms[2];
+    unsigned int aa_frames;
 };
 
 #ifndef GLOME_F32
@@ -1033,6 +1039,7 @@ extern "C" int GLOME_API(glome_scene_destroy)(GlomeScene* s) {
     cudaFree(s->w_counters);
     if (s->aa_counts_host) cudaFreeHost(s->aa_counts_host);
     if (s->aa_ev) cudaEventDestroy(s->aa_ev);
+    for (int k = 0; k < 2; k++) { if (s->aa_t0[k]) cudaEventDestroy(s->aa_t0[k]); if (s->aa_t1[k]) cudaEventDestroy(s->aa_t1[k]); }
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     for (cudaEvent_t e : s->tev) cudaEventDestroy(e);
@@ -1389,6 +1396,7 @@ extern "C" int GLOME_API(glome_render_dev)(GlomeScene* s, const GlomeCamera* cam
     TWIN(glome_render_dev_f32(s, cam, width, height, o, tcolor_dev, rgb8_dev, stats, stream));
     if (!s || !cam || !o || !tcolor_dev || width <= 0 || height <= 0 || o->blocksize <= 0 || o->tile_stride <= 0 ||
         o->tile_first < 0 || o->tile_first >= o->tile_stride) { g_err = "bad argument"; return GLOME_EINVAL; }
+    if (o->mode < GLOME_MODE_ONE_RAY || o->mode > GLOME_MODE_ADAPTIVE_AA_STRICT) { g_err = "bad render mode"; return GLOME_EINVAL; }
     if (o->debug_heatmap && (o->mode != GLOME_MODE_ONE_RAY || o->tint_depth)) {
         g_err = "debug_heatmap is get_color_debug per pixel (Glome.hs:57-60): GLOME_MODE_ONE_RAY without tint_depth only";
         return GLOME_EINVAL;
@@ -1467,27 +1475,55 @@ extern "C" int GLOME_API(glome_render_dev)(GlomeScene* s, const GlomeCamera* cam
             // once, up front, and the per-pass decisions copy from that buffer.  get_color is a pure function of the
             // sample position, so the frame is bit-identical to the adaptive schedule; only the ray count differs.
             bool speculate = !s->use_wave && !s->env_no_speculate;
+            int tune = -1;  // flat scenes: the schedule this frame is a timing sample of (-1: none)
+            if (o->mode == GLOME_MODE_ADAPTIVE_AA_STRICT) speculate = false;
             if (s->use_wave) {
                 // Flat scenes: a wave is cheap per ray but five dependent waves are not (each sits on its latency
                 // floor), so the same speculation pays when the adaptive schedule ends up tracing most pixel centres
                 // anyway (a cloud of small spheres: 95 %) and costs rays when it does not (a smooth mesh: 30 %).
                 // The schedule of this frame follows what the previous frame of the same geometry did; the frame
                 // itself is bit-identical either way.
+                // That ratio is only the first guess.  Whether four more dependent waves or 2-3x the rays cost more depends on
+                // how many rays this device owns (1/N of the tiles when the frame is sharded: the waves of a small share
+                // sit on their latency floors, and tracing every centre is then the cheaper schedule), so both schedules
+                // are timed on the device and the faster one is kept; the other is re-probed now and then.
+                const bool same_geom = s->aa_valid && s->aa_w == width && s->aa_h == height && s->aa_first == o->tile_first &&
+                                       s->aa_stride == o->tile_stride && s->aa_bs == o->blocksize;
+                if (!same_geom) { s->aa_ms_valid[0] = s->aa_ms_valid[1] = false; s->aa_pending[0] = s->aa_pending[1] = false; s->aa_frames = 0; }
                 if (s->env_aa_speculate >= 0) speculate = s->env_aa_speculate != 0;
-                else if (s->aa_valid && s->aa_w == width && s->aa_h == height && s->aa_first == o->tile_first &&
-                         s->aa_stride == o->tile_stride && s->aa_bs == o->blocksize && event_done(s->aa_ev)) {
-                    long long centres = 0, traced = 0;
-                    for (int k = 0; k < n_sel; k++) {
-                        int ti = o->tile_first + k * o->tile_stride, tx = ti / g.nty, ty = ti % g.nty;
-                        centres += (long long)std::min(g.bs, width - tx * g.bs) * std::min(g.bs, height - ty * g.bs);
-                    }
-                    for (int p = 1; p <= 4; p++) traced += s->aa_counts_host[p];
-                    speculate = (double)traced >= GLOME_AA_SPEC_RATIO * (double)centres;
+                else if (o->mode == GLOME_MODE_ADAPTIVE_AA_STRICT) speculate = false;
+                else {
+                    for (int k = 0; k < 2; k++)
+                        if (s->aa_pending[k] && event_done(s->aa_t1[k])) {
+                            float ms = 0;
+                            if (cudaEventElapsedTime(&ms, s->aa_t0[k], s->aa_t1[k]) == cudaSuccess) { s->aa_ms[k] = ms; s->aa_ms_valid[k] = true; }
+                            else cudaGetLastError();
+                            s->aa_pending[k] = false;
+                        }
+                    if (s->aa_ms_valid[0] && s->aa_ms_valid[1]) {
+                        const int best = s->aa_ms[1] < s->aa_ms[0] ? 1 : 0;
+                        tune = (++s->aa_frames % 128 == 0) ? 1 - best : best;  // re-probe the other schedule now and then
+                    } else if (s->aa_ms_valid[0] || s->aa_ms_valid[1]) {
+                        const int known = s->aa_ms_valid[0] ? 0 : 1;
+                        tune = s->aa_pending[1 - known] ? known : 1 - known;
+                    } else if (same_geom && event_done(s->aa_ev)) {
+                        long long centres = 0, traced = 0;
+                        for (int k = 0; k < n_sel; k++) {
+                            int ti = o->tile_first + k * o->tile_stride, tx = ti / g.nty, ty = ti % g.nty;
+                            centres += (long long)std::min(g.bs, width - tx * g.bs) * std::min(g.bs, height - ty * g.bs);
+                        }
+                        for (int p = 1; p <= 4; p++) traced += s->aa_counts_host[p];
+                        tune = (double)traced >= GLOME_AA_SPEC_RATIO * (double)centres ? 1 : 0;
+                    } else tune = 0;
+                    speculate = tune == 1;
+                    if (s->aa_pending[tune] || !same_geom) tune = -1;  // its last measurement is still in flight; a geometry's first frame (allocations, cold caches) is no sample
                 }
                 if (!s->aa_counts_host) {
                     CK(cudaMallocHost((void**)&s->aa_counts_host, 8 * sizeof(int)));
                     CK(cudaEventCreateWithFlags(&s->aa_ev, cudaEventDisableTiming));
+                    for (int k = 0; k < 2; k++) { CK(cudaEventCreate(&s->aa_t0[k])); CK(cudaEventCreate(&s->aa_t1[k])); }
                 }
+                if (tune >= 0) CK(cudaEventRecord(s->aa_t0[tune], st));
             }
             D.spec = nullptr;
             if (speculate) {
@@ -1524,6 +1560,7 @@ extern "C" int GLOME_API(glome_render_dev)(GlomeScene* s, const GlomeCamera* cam
                 else { P.out = tcolor_dev; if ((rc = launch_trace_c<5>(s, P, st))) return rc; }
             }
             if (s->use_wave) {
+                if (tune >= 0) { CK(cudaEventRecord(s->aa_t1[tune], st)); s->aa_pending[tune] = true; }
                 CK(cudaEventRecord(s->aa_ev, st));
                 s->aa_valid = true;
                 s->aa_w = width; s->aa_h = height; s->aa_first = o->tile_first; s->aa_stride = o->tile_stride; s->aa_bs = o->blocksize;

@@ -616,6 +616,11 @@ __global__ void __launch_bounds__(128, GW_BVH_MINBLOCKS) k_bvh_closest(DScene S,
             Bbox lbb_, rbb_;
             int2 kids;
             ld_bvh(S.bvh, ref, lbb_, rbb_, kids.x, kids.y);
+#ifdef GW_BVH_PREFETCH
+            // both children are one dependent (often DRAM) load away: start them now, before the two box tests decide
+            if (kids.x >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(S.bvh + kids.x));
+            if (kids.y >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(S.bvh + kids.y));
+#endif
             Flt lnearp, lfarp, rnearp, rfarp;
             bbclip_ub_rcp(r.o, rcp, lbb_, lnearp, lfarp);
             bbclip_ub_rcp(r.o, rcp, rbb_, rnearp, rfarp);

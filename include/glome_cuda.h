@@ -209,6 +209,11 @@ typedef struct GlomeCamera { /* Camera pos fwd up right (Scene.hs:35); up/right 
 
 #define GLOME_MODE_ONE_RAY 0     /* renderTile: one get_color per pixel        (Glome.hs:162-176) */
 #define GLOME_MODE_ADAPTIVE_AA 1 /* renderTileSubsample: 5-pass adaptive AA    (Glome.hs:226-323) */
+#define GLOME_MODE_ADAPTIVE_AA_STRICT 2 /* the same frame, and also the reference's ray schedule: passes 1-4 trace exactly the
+                                           samples their decisions ask for.  Mode 1 may instead trace every pixel centre up
+                                           front when that is faster on this device (get_color is a pure function of the
+                                           sample position, so the frame is the same bit for bit; only GlomeRenderStats' ray
+                                           counts differ).  bench.py counts a frame's rays in this mode. */
 
 typedef struct GlomeRenderOpts {
     int32_t mode;          /* GLOME_MODE_*                                                   */
