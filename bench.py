@@ -252,7 +252,7 @@ def measure(X, cfg, steps, warmup, with_cpu, cpu_seconds, setup_report=False):
     rdr.render_frame_dev(want_stats=True)
     rdr.opts.mode = mode
     st = rdr.last_stats
-    for _ in range(4):  # let the schedule choice settle (each schedule is timed once before the faster one is kept)
+    for _ in range(8):  # let the schedule choice settle (each schedule is timed twice before the faster one is kept)
         rdr.render_frame_dev()
         barrier()
     counts = torch.tensor([st.rays_primary, st.rays_shadow, st.rays_secondary, st.overflow_rays], dtype=torch.float64,
@@ -295,6 +295,7 @@ def measure(X, cfg, steps, warmup, with_cpu, cpu_seconds, setup_report=False):
     fam_n = np.zeros(4)
     kt = []
     reps = min(steps, 8)
+    scene.set_option(L.OPT_SEG_CONCURRENT, 0)  # each traversal kernel timed alone (they overlap in the timed frames above)
     for _ in range(reps):
         X.flush.fill_(1)
         torch.cuda.synchronize()
@@ -306,6 +307,7 @@ def measure(X, cfg, steps, warmup, with_cpu, cpu_seconds, setup_report=False):
             fam_n[k] = s1.family_launches[k]
     fam_ms /= reps
     kern_ms = float(np.mean(kt))
+    scene.set_option(L.OPT_SEG_CONCURRENT, 1)
 
     # ---- timed: end to end through the C-ABI with host buffers (e2e) ----
     e2e_ms = []
@@ -424,6 +426,8 @@ def measure(X, cfg, steps, warmup, with_cpu, cpu_seconds, setup_report=False):
                          "peak_source": which, "kernel": gname, "launches_per_frame": g_launch,
                          "kernel_ms_per_frame": g_ms, "avg_launch_ms": g_ms / max(1, g_launch),
                          "share_of_step": g_ms / kern_ms if kern_ms > 0 else None, "frame_kernels_ms": kern_ms,
+                         "timing": "CUDA events around every traversal launch of the reference-schedule frame, segments run one "
+                                   "after the other for this measurement (in the timed frames a Bih and a Mesh segment overlap)",
                          "algorithmic_bytes_per_frame": g_bytes,
                          "family_ms": {names[k]: float(fam_ms[k]) for k in range(4) if fam_n[k] > 0},
                          "visits": {"bih_branch": stl.visits_bih, "prim_tests": stl.tests_prim, "bvh_branch": stl.visits_bvh,

@@ -24,6 +24,7 @@ NODE_TYPE_COUNT = 21
 
 CLASS_GENERAL, CLASS_FLAT = 0, 1
 MODE_ONE_RAY, MODE_ADAPTIVE_AA, MODE_ADAPTIVE_AA_STRICT = 0, 1, 2
+OPT_SEG_CONCURRENT, OPT_AA_SPECULATE = 1, 2
 
 OK, EINVAL, ECUDA, ENODEV, ELIMIT, EBUILD = 0, -1, -2, -3, -4, -5
 HITFLAG_STACK_OVERFLOW, HITFLAG_CSG_OVERFLOW = 1, 2
@@ -106,6 +107,7 @@ SIGNATURES = {
     "glome_device_count": (C.c_int, []),
     "glome_scene_create": (C.c_int, [_P(GlomeFlatScene), C.c_int, _P(_vp)]),
     "glome_scene_create_f32": (C.c_int, [_P(GlomeFlatScene), C.c_int, _P(_vp)]),
+    "glome_scene_set_option": (C.c_int, [_vp, C.c_int, C.c_int]),
     "glome_scene_destroy": (C.c_int, [_vp]),
     "glome_rayint_batch": (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_int, _vp]),
     "glome_shadow_batch": (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_int, _vp]),

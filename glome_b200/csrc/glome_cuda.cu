@@ -667,6 +667,10 @@ struct GlomeScene {  // (global scope: the C-ABI's opaque handle)
     Flt* w_hit_t; int* w_hit_seg; int* w_hit_item; int* w_hit_sub; int* w_hit_flags;
     Flt* w_surf; unsigned int* w_occl; int2* w_squeue; int* w_squeue_count;
     unsigned int* w_counters;  // one work counter per persistent launch of a frame
+    // two closest-hit segments side by side (a Bih next to a Mesh): the second one's own result set, stream and events
+    Flt* w2_hit_t; int* w2_hit_seg; int* w2_hit_item; int* w2_hit_sub; int* w2_hit_flags;
+    cudaStream_t st2; cudaEvent_t ev_fork, ev_join;
+    int env_seg_concurrent;
     int w_counter_next;
     std::vector<cudaEvent_t> tev;  // start/stop pairs around the traversal kernels of the last timed frame
     std::vector<int> tev_family;   // kernel family of each pair (GlomeRenderStats.family_ms)
@@ -683,6 +687,7 @@ struct GlomeScene {  // (global scope: the C-ABI's opaque handle)
     // device: each is timed with its own event pair, harvested without a host sync when a later frame starts
     cudaEvent_t aa_t0[2], aa_t1[2];
     bool aa_pending[2], aa_ms_valid[2];
+    int aa_nsamp[2];  // a schedule's first sample (buffers allocated, caches cold) is discarded
     float aa_ms[2];
     unsigned int aa_frames;
 };
@@ -704,6 +709,7 @@ int glome_render_dev_f32(GlomeScene* s, const GlomeCamera* cam, int width, int h
 int glome_render_f32(GlomeScene* s, const GlomeCamera* cam, int width, int height, const GlomeRenderOpts* o, double* tcolor,
                      uint32_t* rgb8, GlomeRenderStats* stats);
 int64_t glome_scene_launches_f32(GlomeScene* s);
+int glome_scene_set_option_f32(GlomeScene* s, int option, int value);
 }
 #define TWIN(call) do { if (s && s->precision == 32) return call; } while (0)
 #else
@@ -997,6 +1003,7 @@ static int scene_create_impl(GlomeScene* s, const GlomeFlatScene* desc, int devi
     s->env_no_speculate = env_int("GLOME_NO_SPECULATE", 0);
     s->env_aa_speculate = env_int("GLOME_AA_SPECULATE", -1);
     s->env_gen_chunk = env_int("GLOME_GEN_CHUNK", 32);
+    s->env_seg_concurrent = env_int("GLOME_SEG_CONCURRENT", 1);
     if (s->env_gen_chunk < 1) s->env_gen_chunk = 1;
     if (s->env_gen_chunk > 32) s->env_gen_chunk = 32;
     // launch geometry of the persistent kernels: once per scene, so that frames issued from several host threads
@@ -1037,6 +1044,10 @@ extern "C" int GLOME_API(glome_scene_destroy)(GlomeScene* s) {
     cudaFree(s->segs_dev); cudaFree(s->w_hit_t); cudaFree(s->w_hit_seg); cudaFree(s->w_hit_item); cudaFree(s->w_hit_sub);
     cudaFree(s->w_hit_flags); cudaFree(s->w_surf); cudaFree(s->w_occl); cudaFree(s->w_squeue); cudaFree(s->w_squeue_count);
     cudaFree(s->w_counters);
+    cudaFree(s->w2_hit_t); cudaFree(s->w2_hit_seg); cudaFree(s->w2_hit_item); cudaFree(s->w2_hit_sub); cudaFree(s->w2_hit_flags);
+    if (s->st2) cudaStreamDestroy(s->st2);
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_join) cudaEventDestroy(s->ev_join);
     if (s->aa_counts_host) cudaFreeHost(s->aa_counts_host);
     if (s->aa_ev) cudaEventDestroy(s->aa_ev);
     for (int k = 0; k < 2; k++) { if (s->aa_t0[k]) cudaEventDestroy(s->aa_t0[k]); if (s->aa_t1[k]) cudaEventDestroy(s->aa_t1[k]); }
@@ -1302,6 +1313,8 @@ static int wave_reserve(GlomeScene* s, size_t samples) {
     if (s->wave_cap >= samples) return GLOME_OK;
     cudaFree(s->w_hit_t); cudaFree(s->w_hit_seg); cudaFree(s->w_hit_item); cudaFree(s->w_hit_sub); cudaFree(s->w_hit_flags);
     cudaFree(s->w_surf); cudaFree(s->w_occl); cudaFree(s->w_squeue);
+    cudaFree(s->w2_hit_t); cudaFree(s->w2_hit_seg); cudaFree(s->w2_hit_item); cudaFree(s->w2_hit_sub); cudaFree(s->w2_hit_flags);
+    s->w2_hit_t = nullptr; s->w2_hit_seg = s->w2_hit_item = s->w2_hit_sub = s->w2_hit_flags = nullptr;
     s->wave_cap = 0;
     int nl = s->n_scene_lights > 0 ? s->n_scene_lights : 1;
     CK(cudaMalloc((void**)&s->w_hit_t, samples * sizeof(Flt)));
@@ -1312,6 +1325,18 @@ static int wave_reserve(GlomeScene* s, size_t samples) {
     CK(cudaMalloc((void**)&s->w_surf, samples * 6 * sizeof(Flt)));
     CK(cudaMalloc((void**)&s->w_occl, samples * sizeof(unsigned int)));
     CK(cudaMalloc((void**)&s->w_squeue, samples * nl * sizeof(int2)));
+    if (s->segs.size() == 2) {
+        CK(cudaMalloc((void**)&s->w2_hit_t, samples * sizeof(Flt)));
+        CK(cudaMalloc((void**)&s->w2_hit_seg, samples * sizeof(int)));
+        CK(cudaMalloc((void**)&s->w2_hit_item, samples * sizeof(int)));
+        CK(cudaMalloc((void**)&s->w2_hit_sub, samples * sizeof(int)));
+        CK(cudaMalloc((void**)&s->w2_hit_flags, samples * sizeof(int)));
+        if (!s->st2) {
+            CK(cudaStreamCreateWithFlags(&s->st2, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+        }
+    }
     s->wave_cap = samples;
     return GLOME_OK;
 }
@@ -1345,23 +1370,50 @@ static int launch_wave(GlomeScene* s, gwave::WaveParams W, long long max_samples
     W.hit_flags = s->w_hit_flags; W.surf = s->w_surf; W.occl = s->w_occl; W.squeue = s->w_squeue;
     W.squeue_count = s->w_squeue_count; W.stats = (unsigned long long*)s->stats;
     CK(cudaMemsetAsync(s->w_squeue_count, 0, sizeof(int), st));
+    // Two traversal segments (a Bih next to a Mesh -- configs[2] / configs[4]): their closest-hit walks are independent
+    // apart from the fold that joins them (Solid.hs:327-328: nearest, ties to the later element), so they run side by side
+    // on two streams, each into its own result set, and k_merge_hits applies the fold.  A small wave sits on the latency
+    // floor of its slowest ray; side by side the two floors overlap instead of adding up.
+    const bool side_by_side = s->w2_hit_t && s->env_seg_concurrent && s->segs.size() == 2 && s->segs[0].kind != SEG_PRIMS && s->segs[1].kind != SEG_PRIMS;
     for (size_t i = 0; i < s->segs.size(); i++) {
         const Seg& sg = s->segs[i];
+        cudaStream_t st_outer = st;
+        gwave::WaveParams W_outer = W;
+        const int segidx_outer = (int)i;
+        if (side_by_side && i == 0) {  // fork before the first segment is enqueued
+            CK(cudaEventRecord(s->ev_fork, st_outer));
+            CK(cudaStreamWaitEvent(s->st2, s->ev_fork, 0));
+        }
+        // (inside this iteration `st`, `W` and the segment index are those of the lane the segment runs in)
+        cudaStream_t st = (side_by_side && i == 1) ? s->st2 : st_outer;
+        gwave::WaveParams W = W_outer;
+        int segidx = segidx_outer;
+        if (side_by_side && i == 1) {
+            W.hit_t = s->w2_hit_t; W.hit_seg = s->w2_hit_seg; W.hit_item = s->w2_hit_item; W.hit_sub = s->w2_hit_sub; W.hit_flags = s->w2_hit_flags;
+            segidx = 0;  // a fold of its own: every sample gets a record, hit_seg is 0 / -1 (k_merge_hits renames it)
+        }
         if (sg.kind == SEG_BIH) {
             bool linear = (s->segs_linear[i] != 0);
             unsigned int* ctr = s->w_counters + (s->w_counter_next++ & 1023);
             trav_mark(s, st, 0);
-            if (linear) k_bih_traverse<false, true><<<g_bih[1], GW_THREADS, 0, st>>>(s->d, W, (int)i, sg, ctr);
-            else k_bih_traverse<false, false><<<g_bih[0], GW_THREADS, 0, st>>>(s->d, W, (int)i, sg, ctr);
+            if (linear) k_bih_traverse<false, true><<<g_bih[1], GW_THREADS, 0, st>>>(s->d, W, segidx, sg, ctr);
+            else k_bih_traverse<false, false><<<g_bih[0], GW_THREADS, 0, st>>>(s->d, W, segidx, sg, ctr);
             trav_mark(s, st, 0);
         } else if (sg.kind == SEG_MESH) {
             unsigned int* ctr = s->w_counters + (s->w_counter_next++ & 1023);
             trav_mark(s, st, 2);
-            k_bvh_closest<<<g_bvh, 128, 0, st>>>(s->d, W, (int)i, sg, ctr);
+            k_bvh_closest<<<g_bvh, 128, 0, st>>>(s->d, W, segidx, sg, ctr);
             trav_mark(s, st, 2);
         } else {
-            k_prims_closest<<<sgrid, 128, 0, st>>>(s->d, W, (int)i, sg);
+            k_prims_closest<<<sgrid, 128, 0, st>>>(s->d, W, segidx, sg);
         }
+        s->launches++;
+        CK(cudaGetLastError());
+    }
+    if (side_by_side) {
+        CK(cudaEventRecord(s->ev_join, s->st2));
+        CK(cudaStreamWaitEvent(st, s->ev_join, 0));
+        k_merge_hits<<<sgrid, 128, 0, st>>>(W, s->w2_hit_t, s->w2_hit_seg, s->w2_hit_item, s->w2_hit_sub, s->w2_hit_flags, 1);
         s->launches++;
         CK(cudaGetLastError());
     }
@@ -1489,14 +1541,14 @@ extern "C" int GLOME_API(glome_render_dev)(GlomeScene* s, const GlomeCamera* cam
                 // are timed on the device and the faster one is kept; the other is re-probed now and then.
                 const bool same_geom = s->aa_valid && s->aa_w == width && s->aa_h == height && s->aa_first == o->tile_first &&
                                        s->aa_stride == o->tile_stride && s->aa_bs == o->blocksize;
-                if (!same_geom) { s->aa_ms_valid[0] = s->aa_ms_valid[1] = false; s->aa_pending[0] = s->aa_pending[1] = false; s->aa_frames = 0; }
+                if (!same_geom) { s->aa_ms_valid[0] = s->aa_ms_valid[1] = false; s->aa_pending[0] = s->aa_pending[1] = false; s->aa_frames = 0; s->aa_nsamp[0] = s->aa_nsamp[1] = 0; }
                 if (s->env_aa_speculate >= 0) speculate = s->env_aa_speculate != 0;
                 else if (o->mode == GLOME_MODE_ADAPTIVE_AA_STRICT) speculate = false;
                 else {
                     for (int k = 0; k < 2; k++)
                         if (s->aa_pending[k] && event_done(s->aa_t1[k])) {
                             float ms = 0;
-                            if (cudaEventElapsedTime(&ms, s->aa_t0[k], s->aa_t1[k]) == cudaSuccess) { s->aa_ms[k] = ms; s->aa_ms_valid[k] = true; }
+                            if (cudaEventElapsedTime(&ms, s->aa_t0[k], s->aa_t1[k]) == cudaSuccess) { s->aa_ms[k] = ms; s->aa_ms_valid[k] = ++s->aa_nsamp[k] >= 2; }
                             else cudaGetLastError();
                             s->aa_pending[k] = false;
                         }
@@ -1621,6 +1673,18 @@ extern "C" int GLOME_API(glome_render)(GlomeScene* s, const GlomeCamera* cam, in
     if (rgb8) CK(cudaMemcpy(rgb8, s->rgb8, npix * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     if (stats) *stats = local;
     return GLOME_OK;
+}
+
+// Run-time switches of one scene (measurement and A/B runs; the frame never depends on them).
+extern "C" int GLOME_API(glome_scene_set_option)(GlomeScene* s, int option, int value) {
+    TWIN(glome_scene_set_option_f32(s, option, value));
+    if (!s) { g_err = "bad argument"; return GLOME_EINVAL; }
+    switch (option) {
+        case GLOME_OPT_SEG_CONCURRENT: s->env_seg_concurrent = value != 0; return GLOME_OK;
+        case GLOME_OPT_AA_SPECULATE: s->env_aa_speculate = value < 0 ? -1 : (value != 0); return GLOME_OK;
+    }
+    g_err = "unknown scene option";
+    return GLOME_EINVAL;
 }
 
 extern "C" int64_t GLOME_API(glome_scene_launches)(GlomeScene* s) {

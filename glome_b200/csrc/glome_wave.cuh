@@ -696,6 +696,24 @@ __global__ void __launch_bounds__(128, GW_BVH_MINBLOCKS) k_bvh_closest(DScene S,
     wave_flush(P.stats, vals);
 }
 
+// The list fold between two segments that were walked side by side (Solid.hs:327-328: foldl' nearest; of two hits at the
+// same depth the later element's wins, Solid.hs:37-44): segment `seg_b`'s own result set is folded into the wave's.
+__global__ void __launch_bounds__(128) k_merge_hits(WaveParams P, const Flt* __restrict__ bt, const int* __restrict__ bseg,
+                                                    const int* __restrict__ bitem, const int* __restrict__ bsub,
+                                                    const int* __restrict__ bflags, int seg_b) {
+    const long long total = wave_total(P);
+    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < total; s += (long long)gridDim.x * blockDim.x) {
+        int x, y;
+        if (!sample_pixel(P, s, x, y)) continue;
+        const int fl = bflags[s];
+        if (fl) P.hit_flags[s] |= fl;
+        if (bseg[s] < 0) continue;
+        const Flt t = bt[s];
+        if (P.hit_seg[s] >= 0 && P.hit_t[s] < t) continue;  // the earlier segment's hit is strictly nearer
+        P.hit_t[s] = t; P.hit_seg[s] = seg_b; P.hit_item[s] = bitem[s]; P.hit_sub[s] = bsub[s];
+    }
+}
+
 // K1 for a run of loose primitives (group children that are wrapped primitives), list fold order
 __global__ void __launch_bounds__(128) k_prims_closest(DScene S, WaveParams P, int segidx, Seg seg) {
     const long long total = wave_total(P);

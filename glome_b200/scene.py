@@ -471,6 +471,10 @@ class Scene:
         self.precision = precision
         self.scene_class = flat.scene_class
 
+    def set_option(self, option, value):
+        """L.OPT_SEG_CONCURRENT / L.OPT_AA_SPECULATE (include/glome_cuda.h): measurement switches, never the frame."""
+        L.check(self.lib.glome_scene_set_option(self.h, int(option), int(value)))
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.glome_scene_destroy(self.h)

@@ -269,6 +269,14 @@ int glome_scene_destroy(GlomeScene* s);
  * states (RGB 1e-3 max abs away from silhouette pixels; tests/test_gpu_f32.py reports the id agreement rate).
  * Not available through glome_multi_create (shard an FP32 scene with tile_first / tile_stride instead). */
 int glome_scene_create_f32(const GlomeFlatScene* desc, int device, GlomeScene** out);
+/* Run-time switches of one scene, for measurements and A/B runs (a frame never depends on them):
+ *   GLOME_OPT_SEG_CONCURRENT  1 (default): a Bih and a Mesh at the top of a flat scene are walked side by side on two
+ *                             streams; 0: one after the other, so that GlomeRenderStats.family_ms times each kernel alone
+ *   GLOME_OPT_AA_SPECULATE    -1 (default): adaptive AA keeps the faster of its two schedules (timed on the device);
+ *                             0 / 1: always the reference's waves / always every pixel centre up front */
+#define GLOME_OPT_SEG_CONCURRENT 1
+#define GLOME_OPT_AA_SPECULATE 2
+int glome_scene_set_option(GlomeScene* s, int option, int value);
 
 /* rayint sld ray d [] []  (Solid.hs:146-151).  rays = n*6 doubles {ox,oy,oz,dx,dy,dz};
  * tmax = n doubles, or 1 double when tmax_stride == 0. */

@@ -160,18 +160,19 @@ def test_aa_schedule_memory_keeps_the_frame_bit_identical():
         fs = b.flatten(root)
         gs = G.Scene(fs)
         opts = G.render_opts(mode=L.MODE_ADAPTIVE_AA, recurs=rec)
-        f1, _, s1 = gs.render(cam, w, h, opts)   # the geometry's first frame: the reference's schedule, not a timing sample
-        f1b, _, s1b = gs.render(cam, w, h, opts)  # the adaptive schedule's sample
-        f2, _, s2 = gs.render(cam, w, h, opts)   # the probe of the speculative schedule
-        f3, _, s3 = gs.render(cam, w, h, opts)
-        f4, _, s4 = gs.render(cam, w, h, opts)
-        assert f1.tobytes() == f1b.tobytes() == f2.tobytes() == f3.tobytes() == f4.tobytes()
-        assert (s1b.launches, s1b.rays_primary) == (s1.launches, s1.rays_primary)
-        assert s2.launches < s1.launches and s2.rays_primary >= s1.rays_primary
-        assert (s4.launches, s4.rays_primary) in ((s1.launches, s1.rays_primary), (s2.launches, s2.rays_primary))
-        assert (s3.launches, s3.rays_primary) == (s4.launches, s4.rays_primary)   # settled
+        frames, sched = [], []
+        for _ in range(8):  # first frame: the reference's schedule; then two timing samples of each; then the faster one
+            f, _, st = gs.render(cam, w, h, opts)
+            frames.append(f.tobytes())
+            sched.append((st.launches, st.rays_primary))
         fs_, _, ss = gs.render(cam, w, h, G.render_opts(mode=L.MODE_ADAPTIVE_AA_STRICT, recurs=rec))
-        assert fs_.tobytes() == f1.tobytes() and (ss.launches, ss.rays_primary) == (s1.launches, s1.rays_primary)
+        strict = (ss.launches, ss.rays_primary)
+        assert all(f == frames[0] for f in frames) and fs_.tobytes() == frames[0]
+        assert sched[0] == strict and strict in sched and len(set(sched)) == 2   # both schedules were tried ...
+        other = [x for x in set(sched) if x != strict][0]
+        assert other[0] < strict[0] and other[1] >= strict[1]                     # ... the other one: fewer waves, more rays
+        assert sched[6] == sched[7]                                               # settled
+        f2 = np.frombuffer(frames[0], dtype=np.float64).reshape(h, w, 5)
         if config == 2:  # and both schedules equal the oracle on a sample of tiles
             osc = O.OracleScene(fs)
             rects = O.tile_rects(w, h, 65)
