@@ -108,6 +108,7 @@ SIGNATURES = {
     "glome_scene_create": (C.c_int, [_P(GlomeFlatScene), C.c_int, _P(_vp)]),
     "glome_scene_create_f32": (C.c_int, [_P(GlomeFlatScene), C.c_int, _P(_vp)]),
     "glome_scene_set_option": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "glome_build_release_cache": (C.c_int, [C.c_int]),
     "glome_scene_destroy": (C.c_int, [_vp]),
     "glome_rayint_batch": (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_int, _vp]),
     "glome_shadow_batch": (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_int, _vp]),

@@ -18,6 +18,8 @@
 #include <cuda_runtime.h>
 
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -632,15 +634,62 @@ __global__ void k_mesh_emit(int n_nodes, const MNodeD* __restrict__ nodes, const
     }
 }
 
+// Work space of a build.  cudaMalloc / cudaFree of the ~0.5 GB a 10^6-item build touches cost several times the build
+// itself (BENCH_r01: 6 ms on the device, 67 ms wall), so freed blocks go to a per-device cache (power-of-two size
+// classes) and the next build of a similar size allocates nothing.  glome_build_release_cache() gives the memory back.
+struct BlockCache {
+    std::mutex mu;
+    std::multimap<size_t, void*> free_blocks[64];  // per device: size class -> block
+    size_t cached_bytes[64] = {0};
+};
+static BlockCache& block_cache() { static BlockCache c; return c; }
+static const size_t BUILD_CACHE_LIMIT = (size_t)8 << 30;  // per device
+
 struct DevMem {
-    std::vector<void*> ptrs;
-    ~DevMem() { for (void* p : ptrs) cudaFree(p); }
+    int device;
+    std::vector<std::pair<size_t, void*>> blocks;
+    explicit DevMem(int dev) : device(dev & 63) {}
+    ~DevMem() {
+        BlockCache& C = block_cache();
+        std::lock_guard<std::mutex> g(C.mu);
+        for (auto& b : blocks) {
+            if (C.cached_bytes[device] + b.first > BUILD_CACHE_LIMIT) { cudaFree(b.second); continue; }
+            C.free_blocks[device].insert(b);
+            C.cached_bytes[device] += b.first;
+        }
+    }
     template <typename T> T* alloc(size_t count) {
+        size_t want = (count ? count : 1) * sizeof(T), cls = 256;
+        while (cls < want) cls <<= 1;
+        {
+            BlockCache& C = block_cache();
+            std::lock_guard<std::mutex> g(C.mu);
+            auto it = C.free_blocks[device].find(cls);
+            if (it != C.free_blocks[device].end()) {
+                void* p = it->second;
+                C.free_blocks[device].erase(it);
+                C.cached_bytes[device] -= cls;
+                blocks.push_back({cls, p});
+                return (T*)p;
+            }
+        }
         void* p = nullptr;
-        cudaError_t e = cudaMalloc(&p, (count ? count : 1) * sizeof(T));
+        cudaError_t e = cudaMalloc(&p, cls);
+        if (e != cudaSuccess) {  // out of memory with blocks parked in the cache: give them back and try once more
+            cudaGetLastError();
+            release_cache(device);
+            e = cudaMalloc(&p, cls);
+        }
         if (e != cudaSuccess) throw BuildError(std::string("bih_build_gpu: cudaMalloc: ") + cudaGetErrorString(e));
-        ptrs.push_back(p);
+        blocks.push_back({cls, p});
         return (T*)p;
+    }
+    static void release_cache(int dev) {
+        BlockCache& C = block_cache();
+        std::lock_guard<std::mutex> g(C.mu);
+        for (auto& b : C.free_blocks[dev & 63]) cudaFree(b.second);
+        C.free_blocks[dev & 63].clear();
+        C.cached_bytes[dev & 63] = 0;
     }
 };
 
@@ -662,7 +711,7 @@ static void bih_build_gpu_impl(int64_t n64, const double* bboxes, int device, Bi
         if (timings_ms) timings_ms[0] = timings_ms[1] = timings_ms[2] = 0;
         return;
     }
-    DevMem M;
+    DevMem M(device);
     const int max_nodes = 3 * n + 4096;
     double* d_bb = M.alloc<double>(6 * (size_t)n);
     double* d_mid = M.alloc<double>(3 * (size_t)n);
@@ -778,7 +827,7 @@ static void mesh_build_gpu_impl(int64_t nverts64, const double* verts, int64_t n
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) throw BuildError("mesh_build_gpu: no such CUDA device");
     BK(cudaSetDevice(device));
-    DevMem M;
+    DevMem M(device);
     const int max_nodes = 3 * n + 4096;
     double* d_verts = M.alloc<double>(3 * (size_t)nverts);
     int* d_tris = M.alloc<int>(8 * (size_t)n);
@@ -882,6 +931,16 @@ static void mesh_build_gpu_impl(int64_t nverts64, const double* verts, int64_t n
         timings_ms[0] = a; timings_ms[1] = b; timings_ms[2] = c;
     }
 }
+
+}  // namespace glome_host
+// give the builders' cached device work space of `device` back to the driver (it is otherwise kept for the next build)
+extern "C" int glome_build_release_cache(int device) {
+    if (device < 0 || device > 63) return GLOME_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return GLOME_ENODEV; }
+    glome_host::DevMem::release_cache(device);
+    return GLOME_OK;
+}
+namespace glome_host {
 
 // libglomecuda.so hands its builders to libglomehost.so when it is loaded (host_base.cpp)
 extern void (*hook_bih_build_gpu)(int64_t, const double*, int, BihTree&, double*);

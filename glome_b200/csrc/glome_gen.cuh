@@ -369,9 +369,36 @@ enum { GI_DEAD = 0, GI_PRIM = 1, GI_INST_PRIM = 2, GI_COMPLEX = 3 };
 
 // the primitive tests of the machine: rayint with position + normal, and shadow.  (rx, ry, rz) = 1 / ray.d, computed
 // once per ray by the caller (only the box uses it).
+#ifdef GQ_RARE_CALL
+// the primitive kinds that are rare in a list next to spheres, boxes and planes: out of line, so that the list loop's
+// own code stays small (the loop is instruction-fetch bound, profiles/README.md)
+GD_NOINLINE bool gq_prim_rayint_rare(const DScene& S, int type, int payload, const Ray& r, Flt d, Flt& t, Vec& pos, Vec& n) {
+    const Flt* p = S.dpool + payload;
+    switch (type) {
+        case GLOME_TRIANGLE: {
+            Vec z = vec(0, 0, 0);
+            return prim_triangle<true>(ldv(p), ldv(p + 3), ldv(p + 6), false, z, z, z, r, d, t, pos, n);
+        }
+        case GLOME_TRIANGLENORM:
+            return prim_triangle<true>(ldv(p), ldv(p + 3), ldv(p + 6), true, ldv(p + 9), ldv(p + 12), ldv(p + 15), r, d, t, pos, n);
+        case GLOME_DISC: return prim_disc_v<true>(ldv(p), ldv(p + 3), p[6], r, d, t, pos, n);
+        case GLOME_CYLINDER: return prim_cylinder<true>(p, r, d, t, pos, n);
+        case GLOME_CONE: return prim_cone<true>(p, r, d, t, pos, n);
+    }
+    return false;
+}
+#endif
 GD_FN bool gq_prim_rayint(const DScene& S, int type, int payload, const Ray& r, Flt rx, Flt ry, Flt rz, Flt d, Flt& t, Vec& pos,
                           Vec& n) {
     const Flt* p = S.dpool + payload;
+#ifdef GQ_RARE_CALL
+    switch (type) {
+        case GLOME_SPHERE: return prim_sphere<true>(p, r, d, t, pos, n);
+        case GLOME_BOX: return prim_box_rcp<true>(p, r, rx, ry, rz, d, t, pos, n);
+        case GLOME_PLANE: return prim_plane<true>(p, r, d, t, pos, n);
+    }
+    return gq_prim_rayint_rare(S, type, payload, r, d, t, pos, n);
+#endif
     switch (type) {
         case GLOME_SPHERE: return prim_sphere<true>(p, r, d, t, pos, n);
         case GLOME_TRIANGLE: {
@@ -445,7 +472,14 @@ GD_NOINLINE bool gq_test_simple(const DScene& S, int4 it, Flt ox, Flt oy, Flt oz
 }
 
 // record a simple item's hit: the context stacks plus the item's own wrappers, outermost first (Tex.hs:54,66)
-GD_FN void gq_fill_hit(const DScene& S, GHit& a, const int4& it, int item, const SimpleHit& h, const PStk& ctex, const PStk& ctag,
+// (out of line: it runs only when a candidate wins, and the list loop around it is instruction-fetch bound -- config 1
+// 11.4 -> 10.7 ms on B200; the rarer primitive kinds out of line as well, GQ_RARE_CALL, cost 3-8 %)
+#ifndef GQ_FILL_INLINE
+GD_NOINLINE
+#else
+GD_FN
+#endif
+void gq_fill_hit(const DScene& S, GHit& a, const int4& it, int item, const SimpleHit& h, const PStk& ctex, const PStk& ctag,
                        int& mflags) {
     a.hit = 1; a.t = h.t; a.pos = h.pos; a.norm = h.norm; a.ray = h.ray; a.prim = it.y; a.sub = -1;
     PStk wtx = ctex, wtg = ctag;

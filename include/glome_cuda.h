@@ -493,6 +493,9 @@ int glome_mesh_build_gpu(int64_t nverts, const double* verts, int64_t ntris, con
                          int32_t* n_leafpool_out, int32_t** leafoff_out, int32_t* n_leaves_out,
                          int32_t* root_ref_out, double bb_out[6], double timings_ms[3]);
 void glome_free(void* p);
+/* The GPU tree builders keep their device work space (about 0.5 GB for 10^6 items) for the next build, because allocating
+ * and freeing it costs several times the build itself.  This returns the cached blocks of `device` to the driver. */
+int glome_build_release_cache(int device);
 
 #ifdef __cplusplus
 }
