@@ -415,6 +415,9 @@ __global__ void __launch_bounds__(128, 1) k_trace_samples(DScene S, TraceParams 
 #ifndef GEN_BLOCK_SYNC
 #define GEN_BLOCK_SYNC 0
 #endif
+#ifndef GEN_PHASE_LOCK
+#define GEN_PHASE_LOCK 0  /* needs GEN_BLOCK_SYNC 1 (block-uniform loop trip counts) */
+#endif
 #ifndef GEN_SYNC_ROUNDS
 #define GEN_SYNC_ROUNDS 1  /* 1: the lanes of a warp start their queries together (warp-synchronous rounds) */
 #endif
@@ -480,7 +483,14 @@ __global__ void __launch_bounds__(GEN_THREADS, GEN_MINBLOCKS) k_gen_trace(DScene
         for (;;) {
             bool need = false;
             if (sr.st != ggen::SS_FINISHED) need = ggen::shm_step<false>(S, sr, sh, q, gc, nullptr);
-#if GEN_SYNC_ROUNDS
+#if GEN_PHASE_LOCK
+            // all warps of the block advance their machines in lockstep rounds, so that at any moment the SM fetches the
+            // code of one part of the machine (the kernel is bound by instruction fetch)
+            if (__syncthreads_or(need) == 0) break;
+            while (__syncthreads_or(need && q.st != ggen::GS_DONE)) {
+                if (need && q.st != ggen::GS_DONE) ggen::qvm_step(S, q, sh.q, gc);
+            }
+#elif GEN_SYNC_ROUNDS
             if (__ballot_sync(FULL, need) == 0) break;
             while (__ballot_sync(FULL, need && q.st != ggen::GS_DONE)) {
                 if (need && q.st != ggen::GS_DONE) ggen::qvm_step(S, q, sh.q, gc);
