@@ -48,10 +48,10 @@
 #define GLOME_AA_SPEC_RATIO 0.6  /* flat scenes: speculate AA passes 1-4 when the last frame traced this share of the pixel centres */
 #endif
 #ifndef GEN_THREADS
-#define GEN_THREADS 128
+#define GEN_THREADS 256
 #endif
 #ifndef GEN_MINBLOCKS
-#define GEN_MINBLOCKS 4
+#define GEN_MINBLOCKS 2
 #endif
 
 using namespace gdev;
@@ -413,10 +413,10 @@ __global__ void __launch_bounds__(128, 1) k_trace_samples(DScene S, TraceParams 
 // of the states present in the warp, and coherent neighbours stay in the same state while strangers do not.
 // ---------------------------------------------------------------------------------------------
 #ifndef GEN_BLOCK_SYNC
-#define GEN_BLOCK_SYNC 0
+#define GEN_BLOCK_SYNC 1
 #endif
 #ifndef GEN_PHASE_LOCK
-#define GEN_PHASE_LOCK 0  /* needs GEN_BLOCK_SYNC 1 (block-uniform loop trip counts) */
+#define GEN_PHASE_LOCK 1  /* needs GEN_BLOCK_SYNC 1 (block-uniform loop trip counts) */
 #endif
 #ifndef GEN_SYNC_ROUNDS
 #define GEN_SYNC_ROUNDS 1  /* 1: the lanes of a warp start their queries together (warp-synchronous rounds) */
@@ -488,7 +488,13 @@ __global__ void __launch_bounds__(GEN_THREADS, GEN_MINBLOCKS) k_gen_trace(DScene
             // code of one part of the machine (the kernel is bound by instruction fetch)
             if (__syncthreads_or(need) == 0) break;
             while (__syncthreads_or(need && q.st != ggen::GS_DONE)) {
+#if GEN_PHASE_LOCK == 2
+                if (need && q.st != ggen::GS_DONE) ggen::qvm_step_part<1>(S, q, sh.q, gc);
+                __syncthreads();
+                if (need && q.st != ggen::GS_DONE) ggen::qvm_step_part<2>(S, q, sh.q, gc);
+#else
                 if (need && q.st != ggen::GS_DONE) ggen::qvm_step(S, q, sh.q, gc);
+#endif
             }
 #elif GEN_SYNC_ROUNDS
             if (__ballot_sync(FULL, need) == 0) break;

@@ -319,6 +319,9 @@ gm_done:
 // ---------------------------------------------------------------------------------------------
 // QVM: rayint / shadow
 // ---------------------------------------------------------------------------------------------
+#ifndef GQ_ROUND_BUDGET
+#define GQ_ROUND_BUDGET 0
+#endif
 #define GQ_WORDS 224    /* control stack, 8-byte words */
 #define GQ_SLOTS 12     /* hit slots */
 #define GQ_ADV_CAP 4096 /* rayint_advance re-issues per query before the machine gives up (flagged) */
@@ -570,7 +573,10 @@ GD_FN void qvm_start(QRegs& q, QVM& vm, int root, const Ray& qray, Flt qd, bool 
 
 // One round of the machine: BIH branch steps, then list items, then at most one ENTER and one RET.  The four parts are
 // laid out one after the other so that the lanes of a warp that sit in the same state execute it together.
-GD_FN void qvm_step(const DScene& S, QRegs& q, QVM& vm, GCnt& cnt) {
+// PART 0: the whole round.  PART 1: BRANCH + LIST only, PART 2: ENTER + RET only -- the two halves a phase-locked block
+// runs on either side of a barrier (k_gen_trace, GEN_PHASE_LOCK 2), so that the SM fetches one half's code at a time.
+template <int PART>
+GD_FN void qvm_step_part(const DScene& S, QRegs& q, QVM& vm, GCnt& cnt) {
     unsigned long long* cs = vm.cs;
     GHit* slot = vm.slot;
     int& sp = q.sp; int& nslots = q.nslots; int& acc = q.acc; Flt& acc_t = q.acc_t; bool& acc_hit = q.acc_hit;
@@ -594,8 +600,15 @@ GD_FN void qvm_step(const DScene& S, QRegs& q, QVM& vm, GCnt& cnt) {
     } while (0)
 
 
+    if (PART != 2) {
+#if GQ_ROUND_BUDGET > 0
+    int budget_b = GQ_ROUND_BUDGET, budget_l = GQ_ROUND_BUDGET;  // steps a lane may take in one round (phase-locked blocks)
+#define GQ_BUDGET(b) ((b)-- > 0)
+#else
+#define GQ_BUDGET(b) true
+#endif
     // ---------------- BRANCH: BIH nodes (Bih.hs:340-366 / 516-542) ----------------
-    while (st == GS_BRANCH) {
+    while (st == GS_BRANCH && GQ_BUDGET(budget_b)) {
         cnt.bih++;
         const BihStep bs_ = ld_bih(S.bih, ref);
         const Flt2 sp2 = {bs_.ls, bs_.rs};
@@ -626,7 +639,7 @@ GD_FN void qvm_step(const DScene& S, QRegs& q, QVM& vm, GCnt& cnt) {
         if (ref < 0) GQ_LEAF();
     }
     // ---------------- LIST: the items of a group / BIH leaf (Solid.hs:326-331) ----------------
-    while (st == GS_LIST) {
+    while (st == GS_LIST && GQ_BUDGET(budget_l)) {
         if (li >= ln) { st = GS_RET; break; }
         const int item = li++;
         if (llin) {  // bare sphere of a linear block: no record to chase
@@ -666,6 +679,8 @@ GD_FN void qvm_step(const DScene& S, QRegs& q, QVM& vm, GCnt& cnt) {
         gq_fill_hit(S, slot[acc], it, item, sh_, ctex, ctag, mflags);
         acc_t = sh_.t; acc_hit = true;
     }
+    }  // PART != 2
+    if (PART == 1) return;
     // ---------------- ENTER: dispatch on a node ----------------
     if (st == GS_ENTER) {
         const int4 it = gd_ldg(S.items + ni);
@@ -1183,7 +1198,10 @@ gq_abort:
 #undef GQ_NEED_SLOT
 #undef GQ_SET_ACC
 #undef GQ_LEAF
+#undef GQ_BUDGET
 }
+
+GD_FN void qvm_step(const DScene& S, QRegs& q, QVM& vm, GCnt& cnt) { qvm_step_part<0>(S, q, vm, cnt); }
 
 // Evaluate one query to completion (batch kernels, the pick query, debug counts).
 GD_NOINLINE bool gq_query(const DScene& S, QVM& vm, int root, const Ray& qray, Flt qd, bool shadow_q, GCnt& cnt) {
