@@ -686,7 +686,7 @@ struct GlomeScene {  // (global scope: the C-ABI's opaque handle)
     // two closest-hit segments side by side (a Bih next to a Mesh): the second one's own result set, stream and events
     Flt* w2_hit_t; int* w2_hit_seg; int* w2_hit_item; int* w2_hit_sub; int* w2_hit_flags;
     cudaStream_t st2; cudaEvent_t ev_fork, ev_join;
-    int env_seg_concurrent;
+    int env_seg_concurrent, env_group_accel;
     int w_counter_next;
     std::vector<cudaEvent_t> tev;  // start/stop pairs around the traversal kernels of the last timed frame
     std::vector<int> tev_family;   // kernel family of each pair (GlomeRenderStats.family_ms)
@@ -962,17 +962,29 @@ static int scene_create_impl(GlomeScene* s, const GlomeFlatScene* desc, int devi
     std::vector<int32_t> ls;
     if (desc->n_lightsets > 0) ls.assign(desc->lightsets, desc->lightsets + 2 * desc->n_lightsets);
     else { ls.push_back(0); ls.push_back(desc->n_lights); }
+    std::vector<GlomeBihNode> bihv;
+    std::vector<double> dpv;
+    const GlomeBihNode* bih_src = desc->bihnodes;
+    const double* dp_src = desc->dpool;
+    size_t bih_n = (size_t)desc->n_bihnodes, dp_n = (size_t)desc->n_dpool;
+    s->env_group_accel = env_int("GLOME_GROUP_ACCEL", 1);
     if (s->scene_class == GLOME_CLASS_GENERAL) {
         // the scene-graph machine packs tag ids into 16 bits: upload dense ids and the table that maps them back
         std::vector<GlomeNode> nodes;
         std::vector<int32_t> ipool, tagvals;
         std::string e = glome_tagmap::remap_tags(desc, nodes, ipool, tagvals);
         if (!e.empty()) { g_err = e; return GLOME_ELIMIT; }
+        std::vector<int32_t> items;
+        glome_tagmap::build_items(nodes, items);
+        if (s->env_group_accel) {  // implicit BIHs over large plain groups: more nodes, items, BIH nodes and two pool records
+            bihv.assign(desc->bihnodes, desc->bihnodes + desc->n_bihnodes);
+            dpv.assign(desc->dpool, desc->dpool + desc->n_dpool);
+            glome_tagmap::build_group_accels(nodes, items, ipool, bihv, dpv);
+            bih_src = bihv.data(); bih_n = bihv.size(); dp_src = dpv.data(); dp_n = dpv.size();
+        }
         if ((rc = upload(s, nodes.data(), nodes.size(), &s->d.nodes))) return rc;
         if ((rc = upload(s, ipool.data(), ipool.size(), &s->d.ipool))) return rc;
         if ((rc = upload(s, tagvals.data(), tagvals.size(), &s->d.tagvals))) return rc;
-        std::vector<int32_t> items;
-        glome_tagmap::build_items(nodes, items);
         const int32_t* items_dev = nullptr;
         if ((rc = upload(s, items.data(), items.size(), &items_dev))) return rc;
         s->d.items = reinterpret_cast<const int4*>(items_dev);
@@ -982,9 +994,9 @@ static int scene_create_impl(GlomeScene* s, const GlomeFlatScene* desc, int devi
     }
 #ifdef GLOME_F32
     {   // FP32 payloads: round every double once, here; refs and indices are unchanged
-        std::vector<DBihNode> bih((size_t)desc->n_bihnodes);
-        for (int i = 0; i < desc->n_bihnodes; i++) {
-            const GlomeBihNode& b = desc->bihnodes[i];
+        std::vector<DBihNode> bih(bih_n);
+        for (size_t i = 0; i < bih_n; i++) {
+            const GlomeBihNode& b = bih_src[i];
             if (b.right > 0x1fffffff || b.right < -0x20000000) { g_err = "FP32 mode: a BIH child ref needs more than 30 bits"; return GLOME_ELIMIT; }
             bih[i].lsplit = (float)b.lsplit; bih[i].rsplit = (float)b.rsplit; bih[i].left = b.left;
             bih[i].right_axis = (int32_t)(((uint32_t)b.right << 2) | (uint32_t)b.axis);
@@ -995,16 +1007,16 @@ static int scene_create_impl(GlomeScene* s, const GlomeFlatScene* desc, int devi
             for (int k = 0; k < 6; k++) { bvh[i].lbb[k] = (float)b.lbb[k]; bvh[i].rbb[k] = (float)b.rbb[k]; }
             bvh[i].left = b.left; bvh[i].right = b.right; bvh[i].pad[0] = bvh[i].pad[1] = 0;
         }
-        std::vector<float> dp((size_t)desc->n_dpool);
-        for (int64_t i = 0; i < desc->n_dpool; i++) dp[(size_t)i] = (float)desc->dpool[i];
+        std::vector<float> dp(dp_n);
+        for (size_t i = 0; i < dp_n; i++) dp[i] = (float)dp_src[i];
         if ((rc = upload(s, bih.data(), bih.size(), &s->d.bih))) return rc;
         if ((rc = upload(s, bvh.data(), bvh.size(), &s->d.bvh))) return rc;
         if ((rc = upload(s, dp.data(), dp.size(), &s->d.dpool))) return rc;
     }
 #else
-    if ((rc = upload(s, desc->bihnodes, (size_t)desc->n_bihnodes, &s->d.bih))) return rc;
+    if ((rc = upload(s, bih_src, bih_n, &s->d.bih))) return rc;
     if ((rc = upload(s, desc->bvhnodes, (size_t)desc->n_bvhnodes, &s->d.bvh))) return rc;
-    if ((rc = upload(s, desc->dpool, (size_t)desc->n_dpool, &s->d.dpool))) return rc;
+    if ((rc = upload(s, dp_src, dp_n, &s->d.dpool))) return rc;
 #endif
     if ((rc = upload(s, desc->textures, (size_t)desc->n_textures, &s->d.textures))) return rc;
     if ((rc = upload(s, desc->materials, (size_t)desc->n_materials, &s->d.materials))) return rc;

@@ -319,6 +319,9 @@ gm_done:
 // ---------------------------------------------------------------------------------------------
 // QVM: rayint / shadow
 // ---------------------------------------------------------------------------------------------
+#ifndef GLOME_GROUP_ACCEL
+#define GLOME_GROUP_ACCEL 2 /* GlomeNode.c of a GROUP: (ipool offset of its implicit-BIH record << 4) | 2 (glome_tagmap.h) */
+#endif
 #ifndef GQ_ROUND_BUDGET
 #define GQ_ROUND_BUDGET 0
 #endif
@@ -543,6 +546,8 @@ struct QRegs {
     int li, ln;             // list registers
     Flt ld;
     bool llin;              // the list is a leaf of a linear-sphere BIH
+    int grp_orig;           // >= 0: cur_bih is the implicit BIH of a plain group (glome_tagmap.h): ipool offset of its list positions
+    int grp_dup, grp_best;  // first copied item of that group; list position of the group's best hit so far (-1: none)
     int ni;
     int st;
 };
@@ -566,6 +571,7 @@ GD_FN void qvm_start(QRegs& q, QVM& vm, int root, const Ray& qray, Flt qd, bool 
     q.drx = 1 / qray.d.x; q.dry = 1 / qray.d.y; q.drz = 1 / qray.d.z;
     q.lin_j0 = 0; q.lin_a0 = -1; q.ref = 0; q.near_ = 0; q.far_ = 0;
     q.li = 0; q.ln = 0; q.ld = 0; q.llin = false;
+    q.grp_orig = -1; q.grp_dup = 0; q.grp_best = -1;
     q.ni = root; q.st = GS_ENTER;
     ghit_clear(vm.slot[0]);
     vm.cs[q.sp++] = gq_hdr(GF_ROOT, 0, 0);
@@ -585,6 +591,7 @@ GD_FN void qvm_step_part(const DScene& S, QRegs& q, QVM& vm, GCnt& cnt) {
     int& cur_bih = q.cur_bih; bool& lin_ok = q.lin_ok; Flt& drx = q.drx; Flt& dry = q.dry; Flt& drz = q.drz;
     int& lin_j0 = q.lin_j0; int& lin_a0 = q.lin_a0; int& ref = q.ref; Flt& near_ = q.near_; Flt& far_ = q.far_;
     int& li = q.li; int& ln = q.ln; Flt& ld = q.ld; bool& llin = q.llin; int& ni = q.ni; int& st = q.st;
+    int& grp_orig = q.grp_orig; int& grp_dup = q.grp_dup; int& grp_best = q.grp_best;
 
 #define GQ_NEED(nw) if (sp + (nw) > GQ_WORDS) { mflags |= GLOME_HITFLAG_CSG_OVERFLOW; goto gq_abort; }
 #define GQ_NEED_SLOT(k) if (nslots + (k) > GQ_SLOTS) { mflags |= GLOME_HITFLAG_CSG_OVERFLOW; goto gq_abort; }
@@ -676,6 +683,11 @@ GD_FN void qvm_step_part(const DScene& S, QRegs& q, QVM& vm, GCnt& cnt) {
 #endif
         if (smode) { retb = true; st = GS_RET; continue; }
         if (acc_hit && acc_t < sh_.t) continue;
+        if (grp_orig >= 0) {  // a plain group walked through its implicit BIH: of equal depths the LATER list element wins
+            const int pos_ = S.ipool[grp_orig + (item - grp_dup)];
+            if (acc_hit && acc_t == sh_.t && grp_best > pos_) continue;
+            grp_best = pos_;
+        }
         gq_fill_hit(S, slot[acc], it, item, sh_, ctex, ctag, mflags);
         acc_t = sh_.t; acc_hit = true;
     }
@@ -706,6 +718,26 @@ GD_FN void qvm_step_part(const DScene& S, QRegs& q, QVM& vm, GCnt& cnt) {
         const GlomeNode nd = S.nodes[ni];
         switch (nd.type) {
             case GLOME_GROUP:  // Solid.hs:327-330
+                if ((nd.c & GLOME_GROUP_ACCEL) && cull && r.d.x != 0 && r.d.y != 0 && r.d.z != 0 &&
+                    fabs_(drx) < FL(1e30) && fabs_(dry) < FL(1e30) && fabs_(drz) < FL(1e30)) {
+                    // a large plain group: walk its implicit BIH (glome_tagmap.h); same hits, list position as the tie key
+                    const int ao = nd.c >> 4;
+                    const Bbox bb = ldbb(S.dpool + S.ipool[ao + 1]);
+                    Flt nr, fr;
+                    bbclip_ub_pre(r, drx, dry, drz, bb, nr, fr);
+                    fr = fmin_(d, fr);
+                    if (nr < 0) nr = 0;
+                    if (nr > fr) { st = GS_RET; break; }  // the ray misses the (padded) box of all elements
+                    GQ_NEED(1);
+                    cs[sp++] = gq_hdr(GF_BIH, cur_bih, 0);
+                    cur_bih = ni;
+                    lin_a0 = -1; lin_ok = true;
+                    grp_orig = S.ipool[ao + 3]; grp_dup = S.ipool[ao + 2]; grp_best = -1;
+                    ref = S.ipool[ao]; near_ = nr; far_ = fr;
+                    if (ref < 0) GQ_LEAF();
+                    else st = GS_BRANCH;
+                    break;
+                }
                 li = nd.a; ln = nd.a + nd.b; ld = d; llin = false; st = GS_LIST;
                 break;
             case GLOME_BIH: {  // Bih.hs:332-338, 368 / 510-515, 544
@@ -868,6 +900,7 @@ GD_FN void qvm_step_part(const DScene& S, QRegs& q, QVM& vm, GCnt& cnt) {
             case GF_BIH:
                 cur_bih = gq_a(h);
                 lin_ok = false;
+                grp_orig = -1;  // (an implicit group BIH holds simple items only, so it is never the OUTER one)
                 break;
             case GF_LIST:
                 sp -= 2;

@@ -6,8 +6,10 @@
 // back when a hit leaves the device.
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <set>
 #include <string>
 #include <unordered_map>
@@ -122,6 +124,152 @@ inline void build_items(const std::vector<GlomeNode>& nodes, std::vector<int32_t
         }
         if (c.type == GLOME_MESH) vis &= ~GI_VIS_S;
         o[0] = GI_COMPLEX | vis | wrapped; o[1] = cj; o[2] = 0; o[3] = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Implicit BIH over large plain groups.
+//
+// `group xs` (Solid.hs:293-302, 326-331) tests every element for every ray: TestScene's chessboard is a group of 64 boxes
+// under a Difference, and about 60 % of that scene's primitive tests are spent there.  The result of the fold is
+// min-depth with ties going to the LATER list element (Solid.hs:37-44), whatever order the elements are visited in, so
+// a group of simple items (`{Tex,Tag}* prim`, `Instance` of one) gets a small BIH of our own over (padded) bounding
+// boxes; the machine walks it like any Bih and keeps the list position as the tie key (glome_gen.cuh).  Rays the BIH
+// arithmetic does not serve exactly like the list would (a zero direction component -- the reference's own Bih misses
+// those, SURVEY A3 -- or a non-unit direction) take the plain list.  rayint_debug, inside and get_metainfo keep reading
+// the group as the list it is.
+//
+// Appends to: nodes / items (copies of the children in leaf order), bih (the tree), dpool (the group's box), ipool
+// (per group {root ref, dpool offset of the box, first copy, offset of the list positions, count} + the positions).
+// The group's node gets c = (ipool offset << 4) | 2.
+// ---------------------------------------------------------------------------------------------
+#ifndef GLOME_GROUP_ACCEL
+#define GLOME_GROUP_ACCEL 2
+#endif
+struct AccelBox { double lo[3], hi[3]; };
+
+inline bool simple_item_box(const std::vector<GlomeNode>& nodes, const int32_t* it, const std::vector<double>& dpool, AccelBox& out) {
+    const int cls = it[0] & 15, type = (it[0] >> 4) & 15;
+    if (cls != GI_PRIM && cls != GI_INST_PRIM) return false;
+    const double* p = dpool.data() + it[2];
+    double lo[3], hi[3];
+    switch (type) {
+        case GLOME_SPHERE: for (int a = 0; a < 3; a++) { lo[a] = p[a] - p[3]; hi[a] = p[a] + p[3]; } break;
+        case GLOME_TRIANGLE: case GLOME_TRIANGLENORM:
+            for (int a = 0; a < 3; a++) { lo[a] = std::min(p[a], std::min(p[3 + a], p[6 + a])); hi[a] = std::max(p[a], std::max(p[3 + a], p[6 + a])); }
+            break;
+        case GLOME_BOX: for (int a = 0; a < 3; a++) { lo[a] = std::min(p[a], p[3 + a]); hi[a] = std::max(p[a], p[3 + a]); } break;
+        case GLOME_DISC: { const double r = std::sqrt(std::fabs(p[6])); for (int a = 0; a < 3; a++) { lo[a] = p[a] - r; hi[a] = p[a] + r; } break; }
+        case GLOME_CYLINDER: lo[0] = lo[1] = -std::fabs(p[0]); hi[0] = hi[1] = std::fabs(p[0]); lo[2] = std::min(p[1], p[2]); hi[2] = std::max(p[1], p[2]); break;
+        case GLOME_CONE: {  // radius r at z = 0 shrinking to 0 at z = height, clipped to [c1, c2]
+            const double h = p[3], r = std::fabs(p[0]);
+            double f = 1;
+            if (h != 0) f = std::max(std::fabs(1 - p[1] / h), std::fabs(1 - p[2] / h));
+            const double rm = r * std::max(1.0, f);
+            lo[0] = lo[1] = -rm; hi[0] = hi[1] = rm; lo[2] = std::min(p[1], p[2]); hi[2] = std::max(p[1], p[2]);
+            break;
+        }
+        default: return false;  // Plane: unbounded
+    }
+    if (cls == GI_INST_PRIM) {  // the eight corners through the forward matrix
+        const double* m = dpool.data() + it[3];
+        double nlo[3] = {1e300, 1e300, 1e300}, nhi[3] = {-1e300, -1e300, -1e300};
+        for (int k = 0; k < 8; k++) {
+            const double x = (k & 1) ? hi[0] : lo[0], y = (k & 2) ? hi[1] : lo[1], z = (k & 4) ? hi[2] : lo[2];
+            for (int a = 0; a < 3; a++) {
+                const double v = m[4 * a] * x + m[4 * a + 1] * y + m[4 * a + 2] * z + m[4 * a + 3];
+                nlo[a] = std::min(nlo[a], v); nhi[a] = std::max(nhi[a], v);
+            }
+        }
+        for (int a = 0; a < 3; a++) { lo[a] = nlo[a]; hi[a] = nhi[a]; }
+    }
+    for (int a = 0; a < 3; a++) {
+        if (!(lo[a] > -1e30 && hi[a] < 1e30) || lo[a] != lo[a] || hi[a] != hi[a]) return false;
+        // padding far above the rounding of any intersection test and of the FP32 twin's payloads
+        const double pad = 1e-3 + 1e-5 * std::max(std::fabs(lo[a]), std::fabs(hi[a]));
+        out.lo[a] = lo[a] - pad; out.hi[a] = hi[a] + pad;
+    }
+    return true;
+}
+
+struct AccelBuild {
+    std::vector<AccelBox> box;
+    std::vector<int> order;          // positions in the list, permuted into leaf order
+    std::vector<GlomeBihNode>* bih;
+    int copy_base;                   // node index of the first copy
+    // returns a child ref: >= 0 node index (global), < 0 inline leaf over copies [lo, hi)
+    int32_t rec(int lo, int hi) {
+        const int n = hi - lo;
+        double clo[3] = {1e300, 1e300, 1e300}, chi[3] = {-1e300, -1e300, -1e300};
+        for (int i = lo; i < hi; i++)
+            for (int a = 0; a < 3; a++) {
+                const double c = 0.5 * (box[order[i]].lo[a] + box[order[i]].hi[a]);
+                clo[a] = std::min(clo[a], c); chi[a] = std::max(chi[a], c);
+            }
+        int ax = 0;
+        for (int a = 1; a < 3; a++) if (chi[a] - clo[a] > chi[ax] - clo[ax]) ax = a;
+        if (n <= 4 || !(chi[ax] - clo[ax] > 0)) {
+            if (n <= 6) return glome_bih_leaf_ref_inline(copy_base + lo, n);
+            // more than six coincident centres: split by position (any split is correct, the planes come from the boxes)
+        }
+        const int mid = lo + n / 2;
+        if (chi[ax] - clo[ax] > 0)
+            std::nth_element(order.begin() + lo, order.begin() + mid, order.begin() + hi, [&](int x, int y) {
+                const double cx = box[x].lo[ax] + box[x].hi[ax], cy = box[y].lo[ax] + box[y].hi[ax];
+                return cx < cy || (cx == cy && x < y);
+            });
+        GlomeBihNode nd;
+        memset(&nd, 0, sizeof(nd));
+        nd.axis = ax;
+        double lmax = -1e300, rmin = 1e300;
+        for (int i = lo; i < mid; i++) lmax = std::max(lmax, box[order[i]].hi[ax]);
+        for (int i = mid; i < hi; i++) rmin = std::min(rmin, box[order[i]].lo[ax]);
+        nd.lsplit = lmax; nd.rsplit = rmin;
+        const int me = (int)bih->size();
+        bih->push_back(nd);
+        const int32_t l = rec(lo, mid), r = rec(mid, hi);
+        (*bih)[me].left = l; (*bih)[me].right = r;
+        return me;
+    }
+};
+
+inline void build_group_accels(std::vector<GlomeNode>& nodes, std::vector<int32_t>& items, std::vector<int32_t>& ipool,
+                               std::vector<GlomeBihNode>& bih, std::vector<double>& dpool, int min_items = 12) {
+    const int n0 = (int)nodes.size();
+    for (int g = 0; g < n0; g++) {
+        if (nodes[g].type != GLOME_GROUP || nodes[g].b < min_items || nodes[g].c != 0) continue;
+        const int first = nodes[g].a, count = nodes[g].b;
+        AccelBuild B;
+        std::vector<int> live;  // list positions that can be hit at all (Void elements never are)
+        bool ok = true;
+        B.box.resize(count);
+        for (int k = 0; k < count && ok; k++) {
+            const int32_t* it = &items[(size_t)(first + k) * 4];
+            if ((it[0] & 15) == GI_DEAD) continue;
+            ok = simple_item_box(nodes, it, dpool, B.box[k]);
+            live.push_back(k);
+        }
+        if (!ok || (int)live.size() < min_items) continue;
+        B.order = live;
+        B.bih = &bih;
+        B.copy_base = (int)nodes.size();
+        const int32_t root = B.rec(0, (int)live.size());
+        // copies of the children in leaf order (a copy's wrapper chain continues into the original nodes)
+        for (size_t i = 0; i < B.order.size(); i++) {
+            const int src = first + B.order[i];
+            nodes.push_back(nodes[src]);
+            for (int q = 0; q < 4; q++) items.push_back(items[(size_t)src * 4 + q]);
+        }
+        if (dpool.size() & 1) dpool.push_back(0);  // 16-byte alignment of the box record
+        const int bb_off = (int)dpool.size();
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (int k : live) for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], B.box[k].lo[a]); hi[a] = std::max(hi[a], B.box[k].hi[a]); }
+        for (int a = 0; a < 3; a++) dpool.push_back(lo[a]);
+        for (int a = 0; a < 3; a++) dpool.push_back(hi[a]);
+        const int ao = (int)ipool.size();
+        ipool.push_back(root); ipool.push_back(bb_off); ipool.push_back(B.copy_base); ipool.push_back(ao + 5); ipool.push_back((int)live.size());
+        for (size_t i = 0; i < B.order.size(); i++) ipool.push_back(B.order[i]);
+        nodes[g].c = (ao << 4) | GLOME_GROUP_ACCEL;
     }
 }
 

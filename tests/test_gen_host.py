@@ -96,3 +96,65 @@ def test_many_csg_crossings_fold_pending_offsets():
     assert np.array_equal(g["pos"], o["pos"]) and np.array_equal(g["norm"], o["norm"])
     assert g["flags"][0] == 2 and g["flags"][2] == 0 and np.array_equal(g["t"][2:], o["t"][2:])
     st = osc.stats()
+
+
+def _tie_group_scene(nested=False):
+    """A plain `group` big enough for the implicit BIH (glome_tagmap.h), full of exact ties: a 6 x 6 board of boxes that
+    share faces (a ray through a shared vertical face meets both at the same depth), every sphere listed twice with
+    different tags, an instanced cone and an instanced box, one Void.  The reference's fold gives equal depths to the LATER
+    list element (Solid.hs:37-44); the tags say which element won."""
+    b = G.SceneBuilder()
+    items, tag = [], 0
+    mat = b.t_matte((0.6, 0.6, 0.6))
+    for i in range(6):
+        for j in range(6):
+            items.append(b.tag(b.box((i, 0, j), (i + 1, 0.5 + 0.25 * ((i + j) % 3), j + 1)), tag)); tag += 1
+    for k in range(5):
+        c, r = (0.7 + 1.1 * k, 1.6, 2.5 + 0.3 * k), 0.45
+        items.append(b.tag(b.sphere(c, r), tag)); tag += 1
+        items.append(b.tag(b.sphere(c, r), tag)); tag += 1   # exact duplicate, listed later: it must win
+    items.append(b.void())
+    items.append(b.tag(b.transform(b.cone((0, 0, 0), 0.5, (0, 1.2, 0), 0.1), [G.translate((3, 1.0, 5.2))]), tag)); tag += 1
+    items.append(b.tag(b.transform(b.box((-0.3, -0.3, -0.3), (0.3, 0.3, 0.3)), [G.rotate((0, 1, 0), 0.4), G.translate((5, 1.5, 1))]), tag)); tag += 1
+    grp = b.group(items)
+    root = b.tex(grp, mat)
+    if nested:  # under an Instance and a Difference, like TestScene's chessboard
+        root = b.tex(b.difference(b.transform(grp, [G.scale((1.5, 1.0, 1.5))]), b.sphere((4, 1.0, 4), 1.3)), mat)
+    b.light((3, 9, -4), (60, 60, 60))
+    b.light((-5, 7, 9), (40, 40, 50))
+    return b, b.flatten(root)
+
+
+def _tie_rays(seed):
+    rng = np.random.default_rng(seed)
+    o = np.column_stack([rng.uniform(-1, 7, 6000), rng.uniform(2.5, 6, 6000), rng.uniform(-1, 7, 6000)])
+    d = np.column_stack([rng.normal(0, 0.4, 6000), -np.abs(rng.normal(1, 0.2, 6000)), rng.normal(0, 0.4, 6000)])
+    # rays that run exactly inside shared faces (x = const planes), axis-parallel rays (zero direction components: the
+    # machine takes the plain list for those), rays along the board
+    k = np.arange(600)
+    face = np.column_stack([1.0 + (k % 5), np.full(600, 4.0), 0.2 + 0.009 * k, np.zeros(600), -np.ones(600), 0.3 * np.sin(k)])
+    down = np.column_stack([0.5 + 0.01 * k, np.full(600, 5.0), 0.5 + 0.009 * k, np.zeros(600), -np.ones(600), np.zeros(600)])
+    flat = np.column_stack([np.full(600, -2.0), 0.3 + 0.001 * k, 0.05 + 0.0098 * k, np.ones(600), 0.01 * np.cos(k), 0.02 * np.sin(k)])
+    rays = np.vstack([np.hstack([o, d]), face, down, flat])
+    rays[:, 3:] /= np.linalg.norm(rays[:, 3:], axis=1)[:, None]
+    return rays
+
+
+@pytest.mark.parametrize("nested", [False, True])
+def test_large_plain_group_keeps_the_list_folds_ties(nested):
+    b, fs = _tie_group_scene(nested)
+    osc, hs = O.OracleScene(fs), H.HostGenScene(fs)
+    rays = _tie_rays(5)
+    o, g = osc.rayint(rays), hs.rayint(rays)
+    same_hits(g, o)
+    assert o["hit"].mean() > 0.4
+    if not nested:  # the duplicated spheres: always the later copy's tag (odd offsets 37, 39, ...)
+        sph = o["hit"].astype(bool) & (o["tag"][:, 0] >= 36) & (o["tag"][:, 0] < 46)
+        assert sph.sum() > 50 and np.all((o["tag"][sph, 0] - 36) % 2 == 1)
+    tmax = np.random.default_rng(6).uniform(1.0, 8.0, len(rays))
+    same_hits(hs.rayint(rays, tmax), osc.rayint(rays, tmax))
+    assert np.array_equal(hs.shadow(rays, 6.0), osc.shadow(rays, 6.0))
+    ro, do = osc.trace(rays, recurs=3)
+    rg, dg = hs.trace(rays, recurs=3)[:2]
+    assert np.array_equal(rg, ro) and np.array_equal(dg, do)
+    assert np.array_equal(hs.debug_count(rays), osc.debug_count(rays))

@@ -2,6 +2,7 @@
 // that its control flow (the explicit stacks that replaced the reference's recursion) can be checked against the oracle
 // on a machine without a GPU.  Built by tests/ into tests/tools/_build/libgenhost.so; nothing under glome_b200/ loads,
 // links or calls it, and no GPU test uses it: the product runs the same header inside its sm_100a kernels only.
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -17,6 +18,8 @@ using namespace ggen;
 struct HostScene {
     std::vector<GlomeNode> nodes;
     std::vector<int32_t> ipool, tagvals, lightsets, items;
+    std::vector<GlomeBihNode> bihv;
+    std::vector<double> dpv;
     DScene d;
 };
 
@@ -52,10 +55,16 @@ void* genh_create(const GlomeFlatScene* fs) {
     if (fs->n_lightsets > 0) h->lightsets.assign(fs->lightsets, fs->lightsets + 2 * fs->n_lightsets);
     else { h->lightsets.push_back(0); h->lightsets.push_back(fs->n_lights); }
     glome_tagmap::build_items(h->nodes, h->items);
+    h->bihv.assign(fs->bihnodes, fs->bihnodes + fs->n_bihnodes);
+    h->dpv.assign(fs->dpool, fs->dpool + fs->n_dpool);
+    {   // the implicit BIHs over large plain groups, as glome_scene_create builds them (GLOME_GROUP_ACCEL=0: plain lists)
+        const char* e = getenv("GLOME_GROUP_ACCEL");
+        if (!e || atoi(e) != 0) glome_tagmap::build_group_accels(h->nodes, h->items, h->ipool, h->bihv, h->dpv);
+    }
     memset(&h->d, 0, sizeof(h->d));
     h->d.items = reinterpret_cast<const int4*>(h->items.data());
-    h->d.nodes = h->nodes.data(); h->d.bih = fs->bihnodes; h->d.bvh = fs->bvhnodes; h->d.ipool = h->ipool.data();
-    h->d.dpool = fs->dpool; h->d.textures = fs->textures; h->d.materials = fs->materials; h->d.lights = fs->lights;
+    h->d.nodes = h->nodes.data(); h->d.bih = h->bihv.data(); h->d.bvh = fs->bvhnodes; h->d.ipool = h->ipool.data();
+    h->d.dpool = h->dpv.data(); h->d.textures = fs->textures; h->d.materials = fs->materials; h->d.lights = fs->lights;
     h->d.lightsets = h->lightsets.data(); h->d.tagvals = h->tagvals.data(); h->d.root = fs->root; h->d.n_lights = fs->n_lights;
     return h;
 }
