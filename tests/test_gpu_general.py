@@ -203,3 +203,25 @@ def test_recurs_above_the_tracer_limit_is_refused():
     with pytest.raises(L.GlomeError) as e:
         gs.render(cam, 16, 16, G.render_opts(mode=L.MODE_ONE_RAY, recurs=9))
     assert e.value.code == L.ELIMIT
+
+
+@pytest.mark.parametrize("nested", [False, True])
+def test_large_plain_group_keeps_the_list_folds_ties_on_the_device(nested):
+    """The implicit BIH the device walks for a large plain `group` (glome_tagmap.h) must give the list fold's result,
+    ties included (shared box faces, duplicated spheres, Void, instanced items; tests/test_gen_host.py builds the scene),
+    in FP64 bit for bit; the FP32 twin walks the same structure."""
+    from test_gen_host import _tie_group_scene, _tie_rays
+    b, fs = _tie_group_scene(nested)
+    gs, osc = G.Scene(fs), O.OracleScene(fs)
+    rays = _tie_rays(5)
+    same_hits(gs.rayint(rays), osc.rayint(rays))
+    tmax = np.random.default_rng(6).uniform(1.0, 8.0, len(rays))
+    same_hits(gs.rayint(rays, tmax), osc.rayint(rays, tmax))
+    assert np.array_equal(gs.shadow(rays, 6.0), osc.shadow(rays, 6.0))
+    ro, do = osc.trace(rays, recurs=3)
+    rg, dg = gs.trace(rays, recurs=3)
+    assert np.array_equal(dg, do) and np.abs(rg - ro).max() <= RGB_TOL
+    assert np.array_equal(gs.debug_count(rays), osc.debug_count(rays))
+    g32 = G.Scene(fs, precision=32).rayint(rays)
+    o = osc.rayint(rays)
+    assert ((g32["hit"] == o["hit"]) & (g32["prim"] == o["prim"])).mean() > 0.97
