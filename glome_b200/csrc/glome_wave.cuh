@@ -163,6 +163,9 @@ __device__ __forceinline__ bool unwrap_prim(const DScene& S, int ni, GlomeNode& 
 #ifndef GW_BVH_MINBLOCKS
 #define GW_BVH_MINBLOCKS 6  /* 80 regs, 24 warps/SM: 3 % over 3 blocks (106 regs); the kernel is bound by its ~200 instructions per two-box node, not by occupancy */
 #endif
+#ifndef GW_BVH_REFILL_MIN
+#define GW_BVH_REFILL_MIN 1
+#endif
 #ifndef GW_GUIDED
 #define GW_GUIDED 1  /* guided self-scheduling of the sample list */
 #endif
@@ -566,7 +569,7 @@ __global__ void __launch_bounds__(128, GW_BVH_MINBLOCKS) k_bvh_closest(DScene S,
 
     for (;;) {
         unsigned int idle = __ballot_sync(FULL, !active);
-        if (idle && !nomore) {
+        if (__popc(idle) >= GW_BVH_REFILL_MIN && !nomore) {
             unsigned int base = 0;
             int cnt = __popc(idle);
 #if GW_GUIDED
