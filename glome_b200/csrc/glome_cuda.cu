@@ -678,6 +678,8 @@ struct GlomeScene {  // (global scope: the C-ABI's opaque handle)
     bool use_wave;
     std::vector<gwave::Seg> segs;
     std::vector<int> segs_linear;
+    std::vector<int> segs_reps;   // per segment: k_bih_traverse's branch-phase bound
+    int env_bih_reps;
     gwave::Seg* segs_dev;
     size_t wave_cap;           // samples
     Flt* w_hit_t; int* w_hit_seg; int* w_hit_item; int* w_hit_sub; int* w_hit_flags;
@@ -1036,10 +1038,10 @@ static int scene_create_impl(GlomeScene* s, const GlomeFlatScene* desc, int devi
     if (s->env_gen_chunk > 32) s->env_gen_chunk = 32;
     // launch geometry of the persistent kernels: once per scene, so that frames issued from several host threads
     // (glome_multi_render) never race on a lazily initialised cache
-    s->g_bih[0] = persistent_grid(s, gwave::k_bih_traverse<false, false>, GW_THREADS);
-    s->g_bih[1] = persistent_grid(s, gwave::k_bih_traverse<false, true>, GW_THREADS);
-    s->g_bih[2] = persistent_grid(s, gwave::k_bih_traverse<true, false>, GW_THREADS);
-    s->g_bih[3] = persistent_grid(s, gwave::k_bih_traverse<true, true>, GW_THREADS);
+    s->g_bih[0] = persistent_grid(s, gwave::k_bih_traverse<false, false, false>, GW_THREADS);
+    s->g_bih[1] = persistent_grid(s, gwave::k_bih_traverse<false, true, false>, GW_THREADS);
+    s->g_bih[2] = persistent_grid(s, gwave::k_bih_traverse<true, false, false>, GW_THREADS);
+    s->g_bih[3] = persistent_grid(s, gwave::k_bih_traverse<true, true, false>, GW_THREADS);
     s->g_bvh = persistent_grid(s, gwave::k_bvh_closest, 128);
     s->g_gen[0] = persistent_grid(s, k_gen_trace<0>, GEN_THREADS);
     s->g_gen[1] = persistent_grid(s, k_gen_trace<1>, GEN_THREADS);
@@ -1056,6 +1058,25 @@ static int scene_create_impl(GlomeScene* s, const GlomeFlatScene* desc, int devi
         for (size_t i = 0; i < s->segs.size(); i++)
             s->segs_linear.push_back(s->segs[i].kind == gwave::SEG_BIH &&
                                      (desc->nodes[s->segs[i].node].c & GLOME_BIH_LINEAR_SPHERES) ? 1 : 0);
+        s->env_bih_reps = env_int("GLOME_BIH_BOUNDED", -1);
+        for (size_t i = 0; i < s->segs.size(); i++) {
+            // the branch-phase bound pays in deep trees: count the Bih's nodes (walk from its root)
+            int reps = 0;  // 0: unbounded branch phase
+            if (s->segs[i].kind == gwave::SEG_BIH) {
+                long long cnt = 0;
+                std::vector<int32_t> stk;
+                const int32_t root = desc->nodes[s->segs[i].node].a;
+                if (root >= 0) stk.push_back(root);
+                while (!stk.empty() && cnt <= 200000) {
+                    const int32_t r = stk.back(); stk.pop_back(); cnt++;
+                    if (desc->bihnodes[r].left >= 0) stk.push_back(desc->bihnodes[r].left);
+                    if (desc->bihnodes[r].right >= 0) stk.push_back(desc->bihnodes[r].right);
+                }
+                if (cnt > 200000) reps = 1;
+                if (s->env_bih_reps >= 0) reps = s->env_bih_reps;  // A/B: 0 = never bounded, 1 = always
+            }
+            s->segs_reps.push_back(reps);
+        }
         s->use_wave = true;
     }
     return GLOME_OK;
@@ -1424,8 +1445,11 @@ static int launch_wave(GlomeScene* s, gwave::WaveParams W, long long max_samples
             bool linear = (s->segs_linear[i] != 0);
             unsigned int* ctr = s->w_counters + (s->w_counter_next++ & 1023);
             trav_mark(s, st, 0);
-            if (linear) k_bih_traverse<false, true><<<g_bih[1], GW_THREADS, 0, st>>>(s->d, W, segidx, sg, ctr);
-            else k_bih_traverse<false, false><<<g_bih[0], GW_THREADS, 0, st>>>(s->d, W, segidx, sg, ctr);
+            const bool bounded = s->segs_reps[i] != 0;
+            if (linear && bounded) k_bih_traverse<false, true, true><<<g_bih[1], GW_THREADS, 0, st>>>(s->d, W, segidx, sg, ctr);
+            else if (linear) k_bih_traverse<false, true, false><<<g_bih[1], GW_THREADS, 0, st>>>(s->d, W, segidx, sg, ctr);
+            else if (bounded) k_bih_traverse<false, false, true><<<g_bih[0], GW_THREADS, 0, st>>>(s->d, W, segidx, sg, ctr);
+            else k_bih_traverse<false, false, false><<<g_bih[0], GW_THREADS, 0, st>>>(s->d, W, segidx, sg, ctr);
             trav_mark(s, st, 0);
         } else if (sg.kind == SEG_MESH) {
             unsigned int* ctr = s->w_counters + (s->w_counter_next++ & 1023);
@@ -1455,8 +1479,11 @@ static int launch_wave(GlomeScene* s, gwave::WaveParams W, long long max_samples
                 bool linear = (s->segs_linear[i] != 0);
                 unsigned int* ctr = s->w_counters + (s->w_counter_next++ & 1023);
                 trav_mark(s, st, 1);
-                if (linear) k_bih_traverse<true, true><<<g_bih[3], GW_THREADS, 0, st>>>(s->d, W, (int)i, sg, ctr);
-                else k_bih_traverse<true, false><<<g_bih[2], GW_THREADS, 0, st>>>(s->d, W, (int)i, sg, ctr);
+                const bool bounded = s->segs_reps[i] != 0;
+                if (linear && bounded) k_bih_traverse<true, true, true><<<g_bih[3], GW_THREADS, 0, st>>>(s->d, W, (int)i, sg, ctr);
+                else if (linear) k_bih_traverse<true, true, false><<<g_bih[3], GW_THREADS, 0, st>>>(s->d, W, (int)i, sg, ctr);
+                else if (bounded) k_bih_traverse<true, false, true><<<g_bih[2], GW_THREADS, 0, st>>>(s->d, W, (int)i, sg, ctr);
+                else k_bih_traverse<true, false, false><<<g_bih[2], GW_THREADS, 0, st>>>(s->d, W, (int)i, sg, ctr);
                 trav_mark(s, st, 1);
             } else if (sg.kind == SEG_PRIMS) {
                 k_prims_any<<<sgrid, 128, 0, st>>>(s->d, W, sg);

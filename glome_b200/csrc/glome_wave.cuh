@@ -148,6 +148,9 @@ __device__ __forceinline__ bool unwrap_prim(const DScene& S, int ni, GlomeNode& 
 #ifndef GW_POLICY
 #define GW_POLICY 0
 #endif
+#ifndef GW_BRANCH_BOUND
+#define GW_BRANCH_BOUND 8
+#endif
 #ifndef GW_BRANCH_REPS
 #define GW_BRANCH_REPS 2
 #endif
@@ -182,7 +185,7 @@ __device__ __forceinline__ bool unwrap_prim(const DScene& S, int ni, GlomeNode& 
 #define GW_STEAL 1   /* drain-phase subtree donation between the lanes of a warp */
 #endif
 
-template <bool ANY, bool LINEAR>
+template <bool ANY, bool LINEAR, bool BOUNDED>
 __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScene S, WaveParams P, int segidx, Seg seg, unsigned int* counter) {
     const unsigned int FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -424,8 +427,13 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScen
         const bool do_branch = __popc(mb) >= __popc(ml);
         for (int rep = 0; rep < GW_BRANCH_REPS && do_branch && active && !done && ref >= 0; rep++) {
 #else
+        // while-while with a BOUNDED branch phase: at most P.branch_reps steps, then the lanes that sit on a leaf do it while
+        // the others keep their place -- in a deep tree (10^6 small spheres) no lane should wait for the deepest descent of
+        // its warp (reps = 8: config 1 4.09 -> 3.79 ms); a shallow tree of large spheres is better off unbounded
+        // (configs[4]: 6.53 vs 6.68 ms), so the host picks the variant per Bih (glome_cuda.cu: launch_wave).  The bound is a
+        // compile-time constant: as a kernel argument it gives half of the gain.
         const bool do_branch = false;
-        while (active && !done && ref >= 0) {
+        for (int rep = 0; (!BOUNDED || rep < GW_BRANCH_BOUND) && active && !done && ref >= 0; rep++) {
 #endif
 #ifndef GW_NOCOUNT
             n_bih++;
