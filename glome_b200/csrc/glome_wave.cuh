@@ -181,6 +181,9 @@ __device__ __forceinline__ bool unwrap_prim(const DScene& S, int ni, GlomeNode& 
 #ifndef GW_STEAL_AFTER
 #define GW_STEAL_AFTER 0
 #endif
+#ifndef GW_BVH_STEAL
+#define GW_BVH_STEAL 1  /* the same for k_bvh_closest */
+#endif
 #ifndef GW_STEAL
 #define GW_STEAL 1   /* drain-phase subtree donation between the lanes of a warp */
 #endif
@@ -574,6 +577,20 @@ __global__ void __launch_bounds__(128, GW_BVH_MINBLOCKS) k_bvh_closest(DScene S,
     unsigned int next_base = 0;
     const long long nwarps = (long long)gridDim.x * 4;
 #endif
+#if GW_BVH_STEAL
+    // drain-phase groups, as in k_bih_traverse: the lanes of one warp that work on the same ray fold their partial
+    // results here; the lane that brings g_pend to 0 writes the sample's result
+    __shared__ Flt g_t[128];
+    __shared__ int g_sub[128], g_pend[128], g_ovf[128], g_tie[128];
+    __shared__ long long g_s[128];
+    __shared__ unsigned long long g_cull[128];
+    const int gb = threadIdx.x & ~31;
+    int grp = -1;       // root lane of the group this lane is a member of
+    int sb = 0;         // live stack entries are [sb, sp): the drain phase donates from the bottom
+    bool solo = false;  // this lane re-walks a ray alone (after a tie) and must not donate
+#else
+    const int sb = 0;
+#endif
 
     for (;;) {
         unsigned int idle = __ballot_sync(FULL, !active);
@@ -607,6 +624,9 @@ __global__ void __launch_bounds__(128, GW_BVH_MINBLOCKS) k_bvh_closest(DScene S,
                         rcp = vrcp(r.d);
                         bbclip_ub_rcp(r.o, rcp, bb, near_, far_);
                         ref = root; sp = 0;
+#if GW_BVH_STEAL
+                        sb = 0;
+#endif
                         active = true;
                         // Mesh.hs:140: root reject (the fold's earlier results stay as they are)
                         if (near_ > far_ || near_ > depth || far_ < 0) {
@@ -617,6 +637,104 @@ __global__ void __launch_bounds__(128, GW_BVH_MINBLOCKS) k_bvh_closest(DScene S,
                 }
             }
         }
+#if GW_BVH_STEAL
+        // ---- drain phase (see k_bih_traverse): the sample list is exhausted, so an idle lane can only help a neighbour.
+        // A ray that grazes the surface walks hundreds of nodes at ~0.4 us of dependent latency each, and a small wave (an AA
+        // pass, 1/N of a frame) sat at 0.2-0.3 ms = its longest ray.  A pushed subtree is independent given (ray, near, far):
+        // the walk's best hit only culls.  So a busy lane donates the oldest entry of its stack to an idle lane of its warp.
+        // The walk order only matters between two different triangles at exactly the same depth (the later one wins,
+        // Mesh.hs:172-176 / Solid.hs:37-44): the fold notes such a tie and the lane that completes the group walks the ray
+        // once more, alone and in order.
+        if (nomore && active && grp >= 0) {
+            if (has) atomicMin(&g_cull[gb + grp], flt_key(best_t));
+            const Flt c = key_flt(g_cull[gb + grp]);
+            if (c < best_t) { best_t = c; has = true; best_sub = -1; }  // own hit is dominated: drop it
+        }
+        if (nomore && idle) {
+            unsigned int fin = __ballot_sync(FULL, !active && grp >= 0);  // finished members: fold in
+            while (fin) {
+                const int l = __ffs(fin) - 1;
+                fin &= fin - 1;
+                if (lane == l) {
+                    const int g = gb + grp;
+                    if (best_sub >= 0 && g_sub[g] >= 0 && g_sub[g] != best_sub && g_t[g] == best_t) g_tie[g] = 1;
+                    if (best_sub >= 0 && (g_sub[g] < 0 || !(g_t[g] < best_t))) { g_t[g] = best_t; g_sub[g] = best_sub; }
+                    g_ovf[g] |= (int)n_ovf;
+                    n_ovf = 0;
+                    const int left = g_pend[g] - 1;
+                    g_pend[g] = left;
+                    if (left == 0 && g_tie[g]) {
+                        // the order of arrival decided between equal depths: redo this ray sequentially
+                        s = g_s[g];
+                        if (segidx > 0) {
+                            best_seg = P.hit_seg[s];
+                            has = best_seg >= 0;
+                            best_t = has ? P.hit_t[s] : (Flt)GLM_INFINITY;
+                        } else { has = false; best_t = GLM_INFINITY; best_seg = -1; }
+                        best_sub = -1;
+                        bbclip_ub_rcp(r.o, rcp, bb, near_, far_);
+                        ref = root; sp = 0; sb = 0;
+                        n_ovf = (unsigned int)(g_ovf[g] != 0);
+                        solo = true;
+                        active = true;
+                    } else if (left == 0) {
+                        const long long ss = g_s[g];
+                        if (g_sub[g] >= 0) { P.hit_t[ss] = g_t[g]; P.hit_seg[ss] = segidx; P.hit_item[ss] = seg.node; P.hit_sub[ss] = g_sub[g]; }
+                        else if (segidx == 0) { P.hit_t[ss] = GLM_INFINITY; P.hit_seg[ss] = -1; P.hit_item[ss] = seg.node; P.hit_sub[ss] = -1; }
+                        if (segidx == 0) P.hit_flags[ss] = g_ovf[g] ? GLOME_HITFLAG_STACK_OVERFLOW : 0;
+                        else if (g_ovf[g]) P.hit_flags[ss] |= GLOME_HITFLAG_STACK_OVERFLOW;
+                    }
+                    grp = -1;
+                }
+                __syncwarp();
+            }
+            const unsigned int free_ = __ballot_sync(FULL, !active);
+            const bool can_give = active && !solo && sp > sb;
+            const unsigned int donors = __ballot_sync(FULL, can_give);
+            const int np = min(__popc(free_), __popc(donors));
+            if (np > 0) {
+                const unsigned int lt = (1u << lane) - 1;
+                const bool is_thief = !active && __popc(free_ & lt) < np;
+                const bool is_donor = can_give && __popc(donors & lt) < np;
+                int eref = 0;
+                Flt en = 0, ef = 0;
+                if (is_donor) {
+                    eref = stack[sb].ref; en = stack[sb].near_; ef = stack[sb].far_;
+                    sb++;
+                    if (grp < 0) {  // first donation: this lane becomes the root of a group
+                        grp = lane;
+                        g_t[gb + lane] = GLM_INFINITY; g_sub[gb + lane] = -1; g_ovf[gb + lane] = 0; g_s[gb + lane] = s;
+                        g_tie[gb + lane] = 0;
+                        g_pend[gb + lane] = 1;
+                        g_cull[gb + lane] = flt_key(has ? best_t : (Flt)GLM_INFINITY);
+                    }
+                }
+                __syncwarp();
+                if (is_donor) atomicAdd(&g_pend[gb + grp], 1);  // the thief's membership
+                const int src = is_thief ? (int)__fns(donors, 0, __popc(free_ & lt) + 1) : lane;
+                eref = __shfl_sync(FULL, eref, src);
+                en = __shfl_sync(FULL, en, src);
+                ef = __shfl_sync(FULL, ef, src);
+                const Flt ox = __shfl_sync(FULL, r.o.x, src), oy = __shfl_sync(FULL, r.o.y, src), oz = __shfl_sync(FULL, r.o.z, src);
+                const Flt dx = __shfl_sync(FULL, r.d.x, src), dy = __shfl_sync(FULL, r.d.y, src), dz = __shfl_sync(FULL, r.d.z, src);
+                const long long ss = __shfl_sync(FULL, s, src);
+                const int lg = __shfl_sync(FULL, grp, src);
+                const Flt bt = __shfl_sync(FULL, best_t, src);
+                const int hs = __shfl_sync(FULL, (int)has, src);
+                const int bs = __shfl_sync(FULL, best_seg, src);
+                if (is_thief) {
+                    r = mkray(vec(ox, oy, oz), vec(dx, dy, dz));
+                    rcp = vrcp(r.d);
+                    s = ss; grp = lg;
+                    ref = eref; near_ = en; far_ = ef;
+                    sp = 0; sb = 0;
+                    has = hs != 0; best_t = bt; best_seg = bs; best_sub = -1;  // the donor's best only culls
+                    active = true;
+                }
+                __syncwarp();
+            }
+        }
+#endif
         if (__ballot_sync(FULL, active) == 0) {
             if (nomore) break;
             continue;
@@ -657,7 +775,7 @@ __global__ void __launch_bounds__(128, GW_BVH_MINBLOCKS) k_bvh_closest(DScene S,
             } else pop = true;
             if (pop) {
                 for (;;) {
-                    if (sp == 0) { done = true; break; }
+                    if (sp == sb) { done = true; break; }
                     sp--;
                     ref = stack[sp].ref; near_ = stack[sp].near_; far_ = stack[sp].far_;
                     Flt fc = hmin(far_, has ? best_t : (Flt)GLM_INFINITY);
@@ -682,14 +800,19 @@ __global__ void __launch_bounds__(128, GW_BVH_MINBLOCKS) k_bvh_closest(DScene S,
                 }
             }
             for (;;) {
-                if (sp == 0) { done = true; break; }
+                if (sp == sb) { done = true; break; }
                 sp--;
                 ref = stack[sp].ref; near_ = stack[sp].near_; far_ = stack[sp].far_;
                 Flt fc = hmin(far_, has ? best_t : (Flt)GLM_INFINITY);
                 if (!(near_ > fc || fc < 0)) break;
             }
         }
+#if GW_BVH_STEAL
+        if (active && done && grp < 0) {  // (a member of a drain-phase group is folded in at the top of the loop)
+            solo = false;
+#else
         if (active && done) {
+#endif
             if (segidx == 0 || (best_seg == segidx && best_sub >= 0)) {
                 P.hit_t[s] = has ? best_t : (Flt)GLM_INFINITY;
                 P.hit_seg[s] = has ? best_seg : -1;
@@ -699,8 +822,8 @@ __global__ void __launch_bounds__(128, GW_BVH_MINBLOCKS) k_bvh_closest(DScene S,
             if (segidx == 0) P.hit_flags[s] = n_ovf ? GLOME_HITFLAG_STACK_OVERFLOW : 0;
             else if (n_ovf) P.hit_flags[s] |= GLOME_HITFLAG_STACK_OVERFLOW;
             n_ovf = 0;
-            active = false;
         }
+        if (active && done) active = false;
     }
     __syncwarp();
     unsigned int vals[9] = {0, 0, 0, 0, 0, 0, 0, n_bvh, n_tri};

@@ -178,6 +178,64 @@ def test_tie_rule_of_nearest_under_donation(size):
     same_hits(gs.rayint(diag), ho)
 
 
+def mirrored_mesh_scene(ntri, seed):
+    """A Mesh of random triangles, each followed somewhere in the list by its mirror image under x <-> y (own texture and
+    tag).  For a ray with o.x == o.y and d.x == d.y the two intersection computations are the same arithmetic with the x and
+    y terms swapped (the cross products change sign as a whole, the three-term dot products only commute), so a triangle
+    and its mirror image are met at EXACTLY the same depth -- in different leaves of the BVH, so that which one the
+    reference's walk meets later (and `nearest` therefore keeps: Mesh.hs:172-176, Solid.hs:37-44) depends on the walk."""
+    b = G.SceneBuilder()
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-6, 6, (ntri, 1, 3))
+    tri = c + rng.uniform(-1.3, 1.3, (ntri, 3, 3))
+    mir = tri[:, :, [1, 0, 2]]
+    verts = np.concatenate([tri.reshape(-1, 3), mir.reshape(-1, 3)])
+    norms = np.tile(np.array([[0.0, 0.0, -1.0]]), (len(verts), 1))
+    order = rng.permutation(2 * ntri)
+    tris = []
+    for k in order:
+        v = 3 * int(k)
+        tris.append((v, v + 1, v + 2, v, v + 1, v + 2, (k % 4) + (4 if k >= ntri else 0), int(k >= ntri)))
+    texs = [b.t_matte(col) for col in rng.uniform(0.1, 1.0, (8, 3))]
+    mesh = b.mesh(verts, norms, np.array(tris, np.int32), texs, [500, 501])
+    b.light((3, 40, -30), (900, 900, 900))
+    root = b.group([mesh])
+    cam = L.GlomeCamera()
+    cam.pos[:] = (0.0, 0.0, -16.0)
+    cam.fwd[:] = (0.0, 0.0, 1.0)
+    cam.up[:] = (0.0, 0.5, 0.0)
+    cam.right[:] = (0.5, 0.0, 0.0)
+    return b, b.flatten(root), cam
+
+
+@pytest.mark.parametrize("size", [24, 64, 384])
+def test_tie_rule_of_nearest_under_donation_in_a_mesh(size):
+    """k_bvh_closest's drain phase splits a ray's pending subtrees among the lanes of its warp.  The rays of the diagonal
+    pixels of a square frame meet every mirrored pair at exactly the same depth; small frames are all drain phase, the large
+    one mixes both.  Ten renders each: the winner must be the oracle's every time."""
+    b, fs, cam = mirrored_mesh_scene(700, 11)
+    assert fs.scene_class == L.CLASS_FLAT
+    gs, osc = G.Scene(fs), O.OracleScene(fs)
+    idx = np.arange(size)
+    diag = G.camera_rays(cam, size, size, idx, idx)
+    assert np.array_equal(diag[:, 3], diag[:, 4])
+    ho = osc.rayint(diag)
+    assert ho["hit"].sum() > size // 4
+    assert len(np.unique(ho["tag"][ho["hit"] != 0, 0])) == 2   # both a triangle and a mirror image win somewhere
+    opts = G.render_opts(mode=L.MODE_ONE_RAY, recurs=2)
+    to, _ = osc.render(cam, size, size, opts)
+    for rep in range(10):
+        tg, _, st = gs.render(cam, size, size, opts)
+        assert np.abs(tg[..., :4] - to[..., :4]).max() <= RGB_TOL, rep
+        assert np.array_equal(tg[..., 4], to[..., 4])
+    same_hits(gs.rayint(diag), ho)
+    aa = G.render_opts(mode=L.MODE_ADAPTIVE_AA, recurs=2, blocksize=33)
+    to, _ = osc.render(cam, size, size, aa)
+    for rep in range(3):
+        tg, _, st = gs.render(cam, size, size, aa)
+        assert np.abs(tg[..., :4] - to[..., :4]).max() <= RGB_TOL, rep
+
+
 def test_render_and_render_dev_buffers_at_growing_sizes():
     """glome_render and glome_render_dev size their work buffers separately: small host frame, then a large
     device frame with adaptive AA, then a large host frame."""
