@@ -1046,6 +1046,10 @@ static int scene_create_impl(GlomeScene* s, const GlomeFlatScene* desc, int devi
     s->g_gen[0] = persistent_grid(s, k_gen_trace<0>, GEN_THREADS);
     s->g_gen[1] = persistent_grid(s, k_gen_trace<1>, GEN_THREADS);
     s->g_gen[2] = persistent_grid(s, k_gen_trace<5>, GEN_THREADS);
+    {   // A/B: GLOME_GEN_GRID_DIV=2 leaves one block of the general tracer per SM
+        const int gd = env_int("GLOME_GEN_GRID_DIV", 1);
+        if (gd > 1) for (int k = 0; k < 3; k++) s->g_gen[k] = std::max(s->sm_count, s->g_gen[k] / gd);
+    }
     s->g_flat[0] = persistent_grid(s, k_trace_samples<0>, 128);
     s->g_flat[1] = persistent_grid(s, k_trace_samples<1>, 128);
     s->g_flat[2] = persistent_grid(s, k_trace_samples<5>, 128);

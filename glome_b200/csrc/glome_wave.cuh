@@ -548,6 +548,67 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScen
     wave_flush(P.stats, vals);
 }
 
+// bbclip_ub_rcp (Vec.hs:725-741) with the sign tests of the reciprocal known at compile time (OCT bit k: rcp.k > 0);
+// OCT == 8: tested per lane
+template <int OCT>
+__device__ __forceinline__ void bvh_clip(const Vec& o, const Vec& rcp, const Bbox& b, Flt& near_, Flt& far_) {
+    Flt inx, outx, iny, outy, inz, outz;
+    slab(OCT == 8 ? rcp.x > 0 : (OCT & 1) != 0, b.p1.x, b.p2.x, o.x, rcp.x, inx, outx);
+    slab(OCT == 8 ? rcp.y > 0 : (OCT & 2) != 0, b.p1.y, b.p2.y, o.y, rcp.y, iny, outy);
+    slab(OCT == 8 ? rcp.z > 0 : (OCT & 4) != 0, b.p1.z, b.p2.z, o.z, rcp.z, inz, outz);
+    near_ = fmax3(inx, iny, inz);
+    far_ = fmin3(outx, outy, outz);
+}
+
+// The branch phase of rayint_mesh's walk (Mesh.hs:166-198): descend until this lane sits on a leaf or its walk is over.
+// Both children pass the same entry test.  The reference writes it as `near > far || near > depth || far < 0` for the
+// child met first and, for the other, the same with far' = min far (ridepth firstresult) (Mesh.hs:178-182); with the walk's
+// best hit so far as the cull depth (best = 10^6 = depth when there is none; a hit's depth is never negative)
+//   n > min f best  <=>  n > f || n > best      and      min f best < 0  <=>  f < 0,
+// so one symmetric test per child serves both, and only the choice of the child to descend into needs their order.
+template <int OCT>
+__device__ __forceinline__ void bvh_branch_phase(const DScene& S, const Ray& r, const Vec& rcp, bool walks, bool has, Flt best_t,
+                                                 Flt depth, TravEnt* stack, int& sp, int sb, int& ref, Flt& near_, Flt& far_,
+                                                 bool& done, unsigned int& n_bvh, unsigned int& n_ovf) {
+    const Flt best = has ? best_t : (Flt)GLM_INFINITY;
+    while (walks && !done && ref >= 0) {
+        n_bvh++;
+        Bbox lbb_, rbb_;
+        int2 kids;
+        ld_bvh(S.bvh, ref, lbb_, rbb_, kids.x, kids.y);
+#ifdef GW_BVH_PREFETCH
+        if (kids.x >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(S.bvh + kids.x));
+        if (kids.y >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(S.bvh + kids.y));
+#endif
+        Flt lnearp, lfarp, rnearp, rfarp;
+        bvh_clip<OCT>(r.o, rcp, lbb_, lnearp, lfarp);
+        bvh_clip<OCT>(r.o, rcp, rbb_, rnearp, rfarp);
+        const Flt lnear = hmax(near_, lnearp), lfar = hmin(far_, lfarp);
+        const Flt rnear = hmax(near_, rnearp), rfar = hmin(far_, rfarp);
+        const bool vl = !(lnear > lfar || lnear > depth || lfar < 0 || lnear > best);
+        const bool vr = !(rnear > rfar || rnear > depth || rfar < 0 || rnear > best);
+        const bool lfirst = lnear < rnear;
+        if (vl && vr) {
+            if (sp < GW_STACK) {
+                stack[sp].ref = lfirst ? kids.y : kids.x; stack[sp].near_ = lfirst ? rnear : lnear; stack[sp].far_ = lfirst ? rfar : lfar;
+                sp++;
+            } else n_ovf = 1;
+        }
+        if (vl || vr) {
+            const bool gol = vl && (!vr || lfirst);
+            ref = gol ? kids.x : kids.y; near_ = gol ? lnear : rnear; far_ = gol ? lfar : rfar;
+        } else {
+            for (;;) {
+                if (sp == sb) { done = true; break; }
+                sp--;
+                ref = stack[sp].ref; near_ = stack[sp].near_; far_ = stack[sp].far_;
+                const Flt fc = hmin(far_, best);
+                if (!(near_ > fc || fc < 0)) break;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1 for a Mesh segment (rayint_mesh, Mesh.hs:136-198): persistent, per-lane refill.
 // A Mesh casts no shadows (Mesh.hs:210), so there is no any-hit variant.
@@ -567,6 +628,7 @@ __global__ void __launch_bounds__(128, GW_BVH_MINBLOCKS) k_bvh_closest(DScene S,
     long long s = 0;
     Ray r = mkray(vec(0, 0, 0), vec(0, 0, 1));
     Vec rcp = vec(0, 0, 0);
+    int oct = 0;  // bit k: rcp.k > 0 (the sign tests of bbclip_ub_rcp)
     Flt near_ = 0, far_ = 0;
     const Flt depth = GLM_INFINITY;
     Flt best_t = GLM_INFINITY;
@@ -622,6 +684,7 @@ __global__ void __launch_bounds__(128, GW_BVH_MINBLOCKS) k_bvh_closest(DScene S,
                         } else { has = false; best_t = GLM_INFINITY; best_seg = -1; }
                         best_sub = -1;
                         rcp = vrcp(r.d);
+                        oct = (rcp.x > 0 ? 1 : 0) | (rcp.y > 0 ? 2 : 0) | (rcp.z > 0 ? 4 : 0);
                         bbclip_ub_rcp(r.o, rcp, bb, near_, far_);
                         ref = root; sp = 0;
 #if GW_BVH_STEAL
@@ -725,6 +788,7 @@ __global__ void __launch_bounds__(128, GW_BVH_MINBLOCKS) k_bvh_closest(DScene S,
                 if (is_thief) {
                     r = mkray(vec(ox, oy, oz), vec(dx, dy, dz));
                     rcp = vrcp(r.d);
+                    oct = (rcp.x > 0 ? 1 : 0) | (rcp.y > 0 ? 2 : 0) | (rcp.z > 0 ? 4 : 0);
                     s = ss; grp = lg;
                     ref = eref; near_ = en; far_ = ef;
                     sp = 0; sb = 0;
@@ -740,46 +804,24 @@ __global__ void __launch_bounds__(128, GW_BVH_MINBLOCKS) k_bvh_closest(DScene S,
             continue;
         }
         bool done = false;
-        while (active && !done && ref >= 0) {
-            n_bvh++;
-            Bbox lbb_, rbb_;
-            int2 kids;
-            ld_bvh(S.bvh, ref, lbb_, rbb_, kids.x, kids.y);
-#ifdef GW_BVH_PREFETCH
-            // both children are one dependent (often DRAM) load away: start them now, before the two box tests decide
-            if (kids.x >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(S.bvh + kids.x));
-            if (kids.y >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(S.bvh + kids.y));
-#endif
-            Flt lnearp, lfarp, rnearp, rfarp;
-            bbclip_ub_rcp(r.o, rcp, lbb_, lnearp, lfarp);
-            bbclip_ub_rcp(r.o, rcp, rbb_, rnearp, rfarp);
-            Flt lnear = hmax(near_, lnearp), lfar = hmin(far_, lfarp);
-            Flt rnear = hmax(near_, rnearp), rfar = hmin(far_, rfarp);
-            Flt best = has ? best_t : (Flt)GLM_INFINITY;
-            int c1, c2;
-            Flt n1, f1, n2, f2;
-            if (lnear < rnear) { c1 = kids.x; n1 = lnear; f1 = lfar; c2 = kids.y; n2 = rnear; f2 = rfar; }
-            else { c1 = kids.y; n1 = rnear; f1 = rfar; c2 = kids.x; n2 = lnear; f2 = lfar; }
-            bool v1 = !(n1 > f1 || n1 > depth || f1 < 0) && !(has && n1 > best);
-            Flt f2c = hmin(f2, best);
-            bool v2 = !(n2 > f2c || n2 > depth || f2c < 0);
-            bool pop = false;
-            if (v1) {
-                if (v2) {
-                    if (sp < GW_STACK) { stack[sp].ref = c2; stack[sp].near_ = n2; stack[sp].far_ = f2; sp++; }
-                    else n_ovf = 1;
-                }
-                ref = c1; near_ = n1; far_ = f1;
-            } else if (v2) {
-                ref = c2; near_ = n2; far_ = f2;
-            } else pop = true;
-            if (pop) {
-                for (;;) {
-                    if (sp == sb) { done = true; break; }
-                    sp--;
-                    ref = stack[sp].ref; near_ = stack[sp].near_; far_ = stack[sp].far_;
-                    Flt fc = hmin(far_, has ? best_t : (Flt)GLM_INFINITY);
-                    if (!(near_ > fc || fc < 0)) break;
+        {
+            // the branch phase, compiled once per sign pattern of the ray direction: when every lane that walks has the same
+            // one (a camera's rays nearly always do), the slab tests know at compile time which plane of a box is the near one
+            const bool walks = active && ref >= 0;
+            const unsigned int wm = __ballot_sync(FULL, walks);
+            if (wm) {
+                const int o0 = __shfl_sync(FULL, oct, __ffs(wm) - 1);
+                const bool uni = __all_sync(FULL, !walks || oct == o0);
+                switch (uni ? o0 : 8) {
+                    case 0: bvh_branch_phase<0>(S, r, rcp, walks, has, best_t, depth, stack, sp, sb, ref, near_, far_, done, n_bvh, n_ovf); break;
+                    case 1: bvh_branch_phase<1>(S, r, rcp, walks, has, best_t, depth, stack, sp, sb, ref, near_, far_, done, n_bvh, n_ovf); break;
+                    case 2: bvh_branch_phase<2>(S, r, rcp, walks, has, best_t, depth, stack, sp, sb, ref, near_, far_, done, n_bvh, n_ovf); break;
+                    case 3: bvh_branch_phase<3>(S, r, rcp, walks, has, best_t, depth, stack, sp, sb, ref, near_, far_, done, n_bvh, n_ovf); break;
+                    case 4: bvh_branch_phase<4>(S, r, rcp, walks, has, best_t, depth, stack, sp, sb, ref, near_, far_, done, n_bvh, n_ovf); break;
+                    case 5: bvh_branch_phase<5>(S, r, rcp, walks, has, best_t, depth, stack, sp, sb, ref, near_, far_, done, n_bvh, n_ovf); break;
+                    case 6: bvh_branch_phase<6>(S, r, rcp, walks, has, best_t, depth, stack, sp, sb, ref, near_, far_, done, n_bvh, n_ovf); break;
+                    case 7: bvh_branch_phase<7>(S, r, rcp, walks, has, best_t, depth, stack, sp, sb, ref, near_, far_, done, n_bvh, n_ovf); break;
+                    default: bvh_branch_phase<8>(S, r, rcp, walks, has, best_t, depth, stack, sp, sb, ref, near_, far_, done, n_bvh, n_ovf); break;
                 }
             }
         }
