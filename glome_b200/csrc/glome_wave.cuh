@@ -181,6 +181,15 @@ __device__ __forceinline__ bool unwrap_prim(const DScene& S, int ni, GlomeNode& 
 #ifndef GW_STEAL_AFTER
 #define GW_STEAL_AFTER 0
 #endif
+#ifndef GW_BVH_GUIDED_DIV
+#define GW_BVH_GUIDED_DIV 2
+#endif
+#ifndef GW_BVH_GUIDED_MIN
+#define GW_BVH_GUIDED_MIN GW_GUIDED_MIN
+#endif
+#ifndef GW_BVH_PREFETCH
+#define GW_BVH_PREFETCH 0
+#endif
 #ifndef GW_BVH_STEAL
 #define GW_BVH_STEAL 1  /* the same for k_bvh_closest */
 #endif
@@ -576,9 +585,13 @@ __device__ __forceinline__ void bvh_branch_phase(const DScene& S, const Ray& r, 
         Bbox lbb_, rbb_;
         int2 kids;
         ld_bvh(S.bvh, ref, lbb_, rbb_, kids.x, kids.y);
-#ifdef GW_BVH_PREFETCH
+#if GW_BVH_PREFETCH == 1
         if (kids.x >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(S.bvh + kids.x));
         if (kids.y >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(S.bvh + kids.y));
+#elif GW_BVH_PREFETCH == 2
+        // the node of whichever child the two box tests choose is one L2 round trip away: start both lines towards L1 now
+        if (kids.x >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(S.bvh + kids.x));
+        if (kids.y >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(S.bvh + kids.y));
 #endif
         Flt lnearp, lfarp, rnearp, rfarp;
         bvh_clip<OCT>(r.o, rcp, lbb_, lnearp, lfarp);
@@ -660,7 +673,7 @@ __global__ void __launch_bounds__(128, GW_BVH_MINBLOCKS) k_bvh_closest(DScene S,
             unsigned int base = 0;
             int cnt = __popc(idle);
 #if GW_GUIDED
-            cnt = min(cnt, (int)min((long long)GW_MAXBATCH, max((long long)GW_GUIDED_MIN, (total - (long long)next_base) / (2LL * nwarps) + 1)));
+            cnt = min(cnt, (int)min((long long)GW_MAXBATCH, max((long long)GW_BVH_GUIDED_MIN, (total - (long long)next_base) / ((long long)GW_BVH_GUIDED_DIV * nwarps) + 1)));
 #endif
             int leader = __ffs(idle) - 1;
             if (lane == leader) base = atomicAdd(counter, (unsigned int)cnt);
