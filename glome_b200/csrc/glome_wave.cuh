@@ -167,7 +167,7 @@ __device__ __forceinline__ bool unwrap_prim(const DScene& S, int ni, GlomeNode& 
 #define GW_BVH_MINBLOCKS 6  /* 80 regs, 24 warps/SM: 3 % over 3 blocks (106 regs); the kernel is bound by its ~200 instructions per two-box node, not by occupancy */
 #endif
 #ifndef GW_BVH_REFILL_MIN
-#define GW_BVH_REFILL_MIN 1
+#define GW_BVH_REFILL_MIN 16
 #endif
 #ifndef GW_GUIDED
 #define GW_GUIDED 1  /* guided self-scheduling of the sample list */
@@ -180,6 +180,9 @@ __device__ __forceinline__ bool unwrap_prim(const DScene& S, int ni, GlomeNode& 
 #endif
 #ifndef GW_STEAL_AFTER
 #define GW_STEAL_AFTER 0
+#endif
+#ifndef GW_BVH_BOUND
+#define GW_BVH_BOUND 12
 #endif
 #ifndef GW_BVH_GUIDED_DIV
 #define GW_BVH_GUIDED_DIV 2
@@ -580,7 +583,8 @@ __device__ __forceinline__ void bvh_branch_phase(const DScene& S, const Ray& r, 
                                                  Flt depth, TravEnt* stack, int& sp, int sb, int& ref, Flt& near_, Flt& far_,
                                                  bool& done, unsigned int& n_bvh, unsigned int& n_ovf) {
     const Flt best = has ? best_t : (Flt)GLM_INFINITY;
-    while (walks && !done && ref >= 0) {
+    // (GW_BVH_BOUND > 0: at most that many steps, then the lanes that sit on a leaf do it while the others keep their place)
+    for (int rep = 0; (GW_BVH_BOUND == 0 || rep < GW_BVH_BOUND) && walks && !done && ref >= 0; rep++) {
         n_bvh++;
         Bbox lbb_, rbb_;
         int2 kids;
