@@ -37,6 +37,7 @@
 #include <thread>
 #include <vector>
 
+#include <algorithm>
 #include <mutex>
 
 #include "glome_device.cuh"
@@ -550,7 +551,10 @@ struct DecideParams {
                          // "trace this pixel" decision is a copy instead of a queue entry
 };
 
-__global__ void __launch_bounds__(256) k_aa_decide(DecideParams P) {
+#ifndef GK_DECIDE_MINBLOCKS
+#define GK_DECIDE_MINBLOCKS 4  /* 64 regs, 32 warps per SM (79 regs / 24 warps: configs[4] +1 %) */
+#endif
+__global__ void __launch_bounds__(256, GK_DECIDE_MINBLOCKS) k_aa_decide(DecideParams P) {
     int ti = P.tile_first + blockIdx.x * P.tile_stride;
     int xt, yt, tw, th;
     tile_rect(P.g, ti, xt, yt, tw, th);
@@ -1020,6 +1024,51 @@ static int scene_create_impl(GlomeScene* s, const GlomeFlatScene* desc, int devi
     if ((rc = upload(s, desc->bvhnodes, (size_t)desc->n_bvhnodes, &s->d.bvh))) return rc;
     if ((rc = upload(s, dp_src, dp_n, &s->d.dpool))) return rc;
 #endif
+    if (env_int("GLOME_LEAF_INLINE", 1)) {
+        // inline leaf vertices of every Mesh (DScene::leafv).  The leaf pools are walked from each Mesh's BVH; the array spans
+        // the ipool range that holds them (one Mesh: exactly its leaf pool).
+        long long lo = -1, hi = -1;
+        std::vector<std::pair<int32_t, int32_t>> meshes;  // (header offset, root)
+        for (int i = 0; i < desc->n_nodes; i++)
+            if (desc->nodes[i].type == GLOME_MESH) {
+                const GlomeMeshHeader* h = reinterpret_cast<const GlomeMeshHeader*>(desc->ipool + desc->nodes[i].a);
+                meshes.push_back(std::make_pair(desc->nodes[i].a, h->root));
+            }
+        std::sort(meshes.begin(), meshes.end());
+        meshes.erase(std::unique(meshes.begin(), meshes.end()), meshes.end());
+        std::vector<std::pair<int32_t, int32_t>> leaves;  // (ipool offset k of {count, tri...}, header offset)
+        for (size_t m = 0; m < meshes.size(); m++) {
+            std::vector<int32_t> stk(1, meshes[m].second);
+            while (!stk.empty()) {
+                const int32_t r = stk.back(); stk.pop_back();
+                if (r < 0) { leaves.push_back(std::make_pair(~r, meshes[m].first)); continue; }
+                stk.push_back(desc->bvhnodes[r].left);
+                stk.push_back(desc->bvhnodes[r].right);
+            }
+        }
+        for (size_t i = 0; i < leaves.size(); i++) {
+            const long long k = leaves[i].first, n = desc->ipool[k];
+            if (n <= 0) continue;
+            if (lo < 0 || k + 1 < lo) lo = k + 1;
+            if (k + n > hi) hi = k + n;
+        }
+        if (lo >= 0 && (hi - lo + 1) * 9LL * (long long)sizeof(Flt) <= (4LL << 30)) {
+            std::vector<Flt> lv((size_t)(hi - lo + 1) * 9, (Flt)0);
+            for (size_t i = 0; i < leaves.size(); i++) {
+                const long long k = leaves[i].first, n = desc->ipool[k];
+                const GlomeMeshHeader* h = reinterpret_cast<const GlomeMeshHeader*>(desc->ipool + leaves[i].second);
+                for (long long j = 0; j < n; j++) {
+                    const int32_t ti = desc->ipool[k + 1 + j];
+                    const int32_t* t = desc->ipool + h->tris_off + 8 * (long long)ti;
+                    Flt* o = lv.data() + (size_t)(k + 1 + j - lo) * 9;
+                    for (int v = 0; v < 3; v++)
+                        for (int c = 0; c < 3; c++) o[3 * v + c] = (Flt)desc->dpool[h->verts_off + 3LL * t[v] + c];
+                }
+            }
+            if ((rc = upload(s, lv.data(), lv.size(), &s->d.leafv))) return rc;
+            s->d.leafv_base = (int)lo;
+        }
+    }
     if ((rc = upload(s, desc->textures, (size_t)desc->n_textures, &s->d.textures))) return rc;
     if ((rc = upload(s, desc->materials, (size_t)desc->n_materials, &s->d.materials))) return rc;
     if ((rc = upload(s, desc->lights, (size_t)desc->n_lights, &s->d.lights))) return rc;

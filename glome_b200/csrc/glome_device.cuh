@@ -71,6 +71,11 @@ struct DScene {
     const int32_t* __restrict__ lightsets;
     const int32_t* __restrict__ tagvals;  // general-class scenes: dense tag id -> the caller's tag value (glome_gen.cuh)
     const int4* __restrict__ items;       // general-class scenes: one item descriptor per node (glome_tagmap.h)
+    // Mesh leaves with their vertices inline (built at upload): 9 Flt {a, b, c} per leaf-pool slot, indexed by
+    // (ipool position of the slot's triangle index) - leafv_base.  A leaf visit then reads its triangles' vertices from one
+    // contiguous run instead of following triangle index -> Tri record -> three vertices.  nullptr: not built.
+    const Flt* __restrict__ leafv;
+    int leafv_base;
     int root;
     int n_lights;
 };

@@ -845,6 +845,20 @@ __global__ void __launch_bounds__(128, GW_BVH_MINBLOCKS) k_bvh_closest(DScene S,
         if (active && !done && ref < 0) {
             int k = ~ref;
             int ntri = __ldg(S.ipool + k);
+            if (S.leafv) {  // the leaf's triangles with their vertices inline: no dependent index loads (DScene::leafv)
+                const Flt* __restrict__ lv = S.leafv + 9 * (size_t)(k + 1 - S.leafv_base);
+                for (int j = 0; j < ntri; j++, lv += 9) {
+                    n_tri++;
+                    const Vec a = vec(__ldg(lv), __ldg(lv + 1), __ldg(lv + 2));
+                    const Vec b = vec(__ldg(lv + 3), __ldg(lv + 4), __ldg(lv + 5));
+                    const Vec c = vec(__ldg(lv + 6), __ldg(lv + 7), __ldg(lv + 8));
+                    Flt t; Vec pp, nn;
+                    Vec z = vec(0, 0, 0);
+                    if (prim_triangle<false>(a, b, c, false, z, z, z, r, far_, t, pp, nn) && (!has || !(best_t < t))) {
+                        has = true; best_t = t; best_sub = __ldg(S.ipool + k + 1 + j); best_seg = segidx;
+                    }
+                }
+            } else
             for (int j = 0; j < ntri; j++) {
                 int ti = __ldg(S.ipool + k + 1 + j);
                 n_tri++;
@@ -1006,7 +1020,10 @@ __device__ __forceinline__ void load_hit(const DScene& S, const WaveParams& P, c
 }
 
 // K2a: surface point of every hit + shadow-ray queue (mpreshade's per-light tests, Shader.hs:65-80)
-__global__ void __launch_bounds__(128) k_surface(DScene S, WaveParams P, const Seg* __restrict__ segs) {
+#ifndef GW_SURFACE_MINBLOCKS
+#define GW_SURFACE_MINBLOCKS 8  /* 64 regs, 32 warps per SM (88 regs / 20 warps) */
+#endif
+__global__ void __launch_bounds__(128, GW_SURFACE_MINBLOCKS) k_surface(DScene S, WaveParams P, const Seg* __restrict__ segs) {
     const unsigned int FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const long long total = wave_total(P);
@@ -1072,7 +1089,10 @@ __device__ __forceinline__ TCw getcw(const double* __restrict__ v, int width, in
 }
 
 // K2b: trace's texture fold + materialShader for Surface materials (Trace.hs:59-82, Shader.hs:82-105)
-__global__ void __launch_bounds__(128) k_shade(DScene S, WaveParams P, const Seg* __restrict__ segs) {
+#ifndef GW_SHADE_MINBLOCKS
+#define GW_SHADE_MINBLOCKS 4    /* 128 regs, 16 warps per SM (160 regs / 12 warps: configs[2] +2 %, configs[4] +1 %) */
+#endif
+__global__ void __launch_bounds__(128, GW_SHADE_MINBLOCKS) k_shade(DScene S, WaveParams P, const Seg* __restrict__ segs) {
     const long long total = wave_total(P);
     const int lfirst = S.lightsets[0], lcnt = S.lightsets[1];
     unsigned int n_primary = 0, n_ovf = 0, n_perlin = 0;
