@@ -149,7 +149,7 @@ __device__ __forceinline__ bool unwrap_prim(const DScene& S, int ni, GlomeNode& 
 #define GW_POLICY 0
 #endif
 #ifndef GW_BRANCH_BOUND
-#define GW_BRANCH_BOUND 8
+#define GW_BRANCH_BOUND 6
 #endif
 #ifndef GW_BRANCH_REPS
 #define GW_BRANCH_REPS 2
@@ -162,6 +162,9 @@ __device__ __forceinline__ bool unwrap_prim(const DScene& S, int ni, GlomeNode& 
 #endif
 #ifndef GW_REFILL_MIN
 #define GW_REFILL_MIN 16  /* 8 -> 16: +2 % on small waves and on the mesh AA frame, same at full load (r1g A/B) */
+#endif
+#ifndef GW_REFILL_MIN_BOUNDED
+#define GW_REFILL_MIN_BOUNDED 12  /* the bounded-branch-phase variant (deep trees): bound 6 + refill at 12 idle lanes, configs[1] 3.72 -> 3.58 ms */
 #endif
 #ifndef GW_BVH_MINBLOCKS
 #define GW_BVH_MINBLOCKS 6  /* 80 regs, 24 warps/SM: 3 % over 3 blocks (106 regs); the kernel is bound by its ~200 instructions per two-box node, not by occupancy */
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScen
         unsigned int idle = __ballot_sync(FULL, !active);
         // refill in batches: ray set-up (camera ray, root clip, three divisions) is ~200 instructions, so it
         // should run with many lanes at once rather than one lane at a time
-        if (__popc(idle) >= GW_REFILL_MIN && !nomore) {
+        if (__popc(idle) >= (BOUNDED ? GW_REFILL_MIN_BOUNDED : GW_REFILL_MIN) && !nomore) {
             unsigned int base = 0;
             int cnt = __popc(idle);
 #if GW_GUIDED
@@ -444,7 +447,7 @@ __global__ void __launch_bounds__(GW_THREADS, GW_MINBLOCKS) k_bih_traverse(DScen
 #else
         // while-while with a BOUNDED branch phase: at most P.branch_reps steps, then the lanes that sit on a leaf do it while
         // the others keep their place -- in a deep tree (10^6 small spheres) no lane should wait for the deepest descent of
-        // its warp (reps = 8: config 1 4.09 -> 3.79 ms); a shallow tree of large spheres is better off unbounded
+        // its warp (8 steps: config 1 4.09 -> 3.79 ms; 6 steps with the refill threshold at 12 lanes: 3.72 -> 3.58 ms); a shallow tree of large spheres is better off unbounded
         // (configs[4]: 6.53 vs 6.68 ms), so the host picks the variant per Bih (glome_cuda.cu: launch_wave).  The bound is a
         // compile-time constant: as a kernel argument it gives half of the gain.
         const bool do_branch = false;
