@@ -360,7 +360,7 @@ def measure(X, cfg, steps, warmup, with_cpu, cpu_seconds, setup_report=False):
                 ev32.append((e0, e1))
             torch.cuda.synchronize()
             ms32 = sum(a.elapsed_time(bb) for a, bb in ev32) / n32
-            rays32 = st32.rays_primary + st32.rays_shadow + st32.rays_secondary
+            rays32 = rays_frame  # the reference schedule's ray count of this frame (a speculated AA frame traces more; never counted)
             d = (tc32[..., :4] - tc64[..., :4]).abs().amax(dim=-1)
             fp32 = {"dtype": "f32", "ms_per_step": ms32, "fps": 1000.0 / ms32, "value": rays32 / (ms32 * 1e-3) / 1e6,
                     "unit": "Mrays/s", "speedup_over_f64": ms_per_step / ms32,
