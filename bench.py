@@ -409,8 +409,12 @@ def measure(X, cfg, steps, warmup, with_cpu, cpu_seconds, setup_report=False):
                 t = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
                 e = t.get(c["key"])
                 if e:
-                    traffic = e["dram_bytes_per_frame"] / max(1, g_launch)
-                    traffic_src = "committed ncu --set full capture (%s), per launch; not measured in this run" % e["source"]
+                    fam = e.get("families", {}).get(gname.split(" ")[0])  # DRAM bytes per frame of the dominant kernel family
+                    if fam is None and gname.startswith(e.get("kernel", "?")):
+                        fam = e["dram_bytes_per_frame"]
+                    if fam is not None:
+                        traffic = fam / max(1, g_launch)
+                        traffic_src = "committed ncu pass (%s), per launch; not measured in this run" % e["source"]
         except Exception:
             pass
         res = {
